@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- aligned bp scored/s of the chain-rescoring hot path on N B200s of one node.
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): a genome-wide
+synthetic hg38 x mm10 chain set -- all 455 / 66 sequences of example/{hg38,mm10}.chrom.sizes,
+~10 M blocks per GPU, heavy-tailed chain sizes, both strands, N runs, homologous query -- scored
+with the default matrix and -linearGap=medium (global + local score per chain, as scoreChain does).
+
+A step = one pass of the hot path over the rank's whole work-list.  `value` times the kernels with
+the work-list resident in HBM; `e2e` times the public call gat_score() with pinned HOST buffers
+(H2D of the work-list + kernels + D2H of the scores) every step.  Ranks are independent shards
+(weak scaling, no collective on the data path); time is the max over ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--blocks B] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+METRIC = "aligned bp scored/s"
+UNIT = "Gbp/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- workload
+def build_workload(n_blocks, rank, plant=True):
+    from genomealignmenttools_b200 import synth
+    tn, ts = synth.read_chrom_sizes(os.path.join(GOLDEN, "example", "hg38.chrom.sizes"))
+    qn, qs = synth.read_chrom_sizes(os.path.join(GOLDEN, "example", "mm10.chrom.sizes"))
+    t0 = time.time()
+    t = synth.random_genome(tn, ts, 0x5EED0001, telomere_n=10000)
+    q = synth.random_genome(qn, qs, 0x5EED0002, telomere_n=10000)
+    jobs, total, blocks = synth.make_chains(ts, qs, n_blocks, seed=0x5EED0050 + rank)
+    if plant:
+        synth.plant_homology(t, q, jobs, total, blocks, 0.30, 0x5EED0060 + rank)
+    synth.sprinkle_n_runs(t, "t", jobs, blocks, 0.0005, 0x5EED0070 + rank)
+    synth.sprinkle_n_runs(q, "q", jobs, blocks, 0.0005, 0x5EED0080 + rank)
+    w = synth.Workload(t, q, jobs, total, blocks)
+    w.t_names, w.q_names = tn, qn
+    log("[rank %d] workload: %d chains, %d blocks, %.1f Mbp aligned, built in %.1f s"
+        % (rank, len(jobs), total, w.aligned_bp / 1e6, time.time() - t0))
+    return w
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            inside = t_begin - 0.05 <= ts <= t_end + 0.15
+            try:
+                if inside:
+                    sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            if inside:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def sample_for_cpu(w, cores, max_aligned_bp):
+    """A bounded sample of the same workload for the host cores: whole chains on `cores` mid-size
+    target chromosomes x 6 query chromosomes (bounds the reference's whole-chromosome unpacking),
+    one shard per target chromosome = one reference process per core."""
+    t_pick = [w.t_names.index(n) for n in ("chr8", "chr9", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15",
+                                           "chr16", "chr17", "chr18", "chr19", "chr20", "chr21", "chr22", "chrX")
+              if n in w.t_names][:max(1, cores)]
+    q_pick = [w.q_names.index(n) for n in ("chr1", "chr2", "chr3", "chr4", "chr5", "chr6") if n in w.q_names]
+    qs = w.jobs["qSeq"] & np.uint32(0x7FFFFFFF)
+    counts = np.diff(np.append(w.jobs["blockPtr"].astype(np.int64), w.total))
+    csum = np.concatenate([[0], np.cumsum(w.blocks["size"].astype(np.int64))])
+    job_bp = csum[w.jobs["firstBlock"].astype(np.int64) + counts] - csum[w.jobs["firstBlock"].astype(np.int64)]
+    shards = []
+    per_shard = max_aligned_bp // max(1, len(t_pick))
+    for ti in t_pick:
+        sel = np.nonzero((w.jobs["tSeq"] == ti) & np.isin(qs, q_pick))[0]
+        keep = sel[np.cumsum(job_bp[sel]) <= per_shard]
+        if len(keep) == 0 and len(sel):
+            keep = sel[:1]
+        shards.append(keep)
+    return t_pick, q_pick, shards
+
+
+def write_shard_files(w, t_pick, q_pick, shards, d):
+    """Sample .2bit files holding only the touched sequences + one .chain per shard."""
+    from genomealignmenttools_b200.twobit import PackedGenome
+    from genomealignmenttools_b200 import chainio
+
+    def subset(g, names, pick):
+        chunks, offs, cur = [], [], 0
+        for i in pick:
+            nb = (int(g.sizes[i]) + 3) // 4
+            chunks.append(g.packed[int(g.byte_offsets[i]):int(g.byte_offsets[i]) + nb]); offs.append(cur); cur += nb
+        runs = g.n_runs[np.isin(g.n_runs["seq"], pick)].copy()
+        remap = {old: new for new, old in enumerate(pick)}
+        runs["seq"] = [remap[int(s)] for s in runs["seq"]]
+        return PackedGenome([names[i] for i in pick], g.sizes[pick], np.concatenate(chunks), offs, runs)
+
+    t_path, q_path = os.path.join(d, "t.2bit"), os.path.join(d, "q.2bit")
+    subset(w.t, w.t_names, t_pick).write_2bit(t_path)
+    subset(w.q, w.q_names, q_pick).write_2bit(q_path)
+    counts = np.diff(np.append(w.jobs["blockPtr"].astype(np.int64), w.total))
+    paths = []
+    for k, sel in enumerate(shards):
+        heads = []
+        for j in sel:
+            job = w.jobs[j]
+            fb, nb = int(job["firstBlock"]), int(counts[j])
+            first, last = w.blocks[fb], w.blocks[fb + nb - 1]
+            ti, qi = int(job["tSeq"]), int(job["qSeq"] & 0x7FFFFFFF)
+            heads.append((0, w.t_names[ti], int(w.t.sizes[ti]), int(first["tStart"]), int(last["tStart"]) + int(last["size"]),
+                          w.q_names[qi], int(w.q.sizes[qi]), "-" if job["qSeq"] >> 31 else "+",
+                          int(first["qStart"]), int(last["qStart"]) + int(last["size"]), int(j) + 1))
+        p = os.path.join(d, "shard%d.chain" % k)
+        chainio.write_chains(p, heads, w.blocks, w.jobs["firstBlock"][sel], counts[sel])
+        paths.append(p)
+    return t_path, q_path, paths
+
+
+def run_reference_pass(t_path, q_path, chain_paths, reps, want_scores=False):
+    """One ref_driver process per shard, all at once (the reference is single-threaded).  Returns
+    (aligned bp, wall seconds of the slowest process' best scoring pass, per-process dicts)."""
+    procs = []
+    for p in chain_paths:
+        cmd = [REF_DRIVER, p, t_path, q_path, "medium", "-", str(reps)]
+        if want_scores:
+            cmd.append(p + ".scores")
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for pr in procs:
+        so, se = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("ref_driver failed: " + se[-500:])
+        outs.append(json.loads(so.strip().splitlines()[-1]))
+    bp = sum(o["aligned_bp"] for o in outs)
+    return bp, max(o["score_s_best"] for o in outs), outs
+
+
+def cpu_reference(w, steps, warmup, max_aligned_bp, gpu_scores=None):
+    cores = os.cpu_count() or 1
+    if not os.path.exists(REF_DRIVER):
+        return None
+    t_pick, q_pick, shards = sample_for_cpu(w, cores, max_aligned_bp)
+    with tempfile.TemporaryDirectory() as d:
+        t_path, q_path, chain_paths = write_shard_files(w, t_pick, q_pick, shards, d)
+        t0 = time.time()
+        bp, sec, outs = run_reference_pass(t_path, q_path, chain_paths, max(1, steps + warmup), want_scores=True)
+        wall = time.time() - t0
+        checked = mismatches = 0
+        if gpu_scores is not None:
+            g, l = gpu_scores
+            for p in chain_paths:
+                rows = np.loadtxt(p + ".scores", dtype=np.int64, ndmin=2)
+                if rows.size == 0:
+                    continue
+                j = rows[:, 0] - 1
+                mismatches += int((g[j] != rows[:, 1]).sum() + (l[j] != rows[:, 2]).sum())
+                checked += len(j)
+    n_chains = sum(o["chains"] for o in outs)
+    return {"value": bp / sec / 1e9, "unit": UNIT, "cores": len(chain_paths), "kind": "reference",
+            "sample": "%d whole chains (%d blocks, %.1f Mbp aligned) of the same workload on %d target x %d query "
+                      "chromosomes; unmodified getChainScore (chainCalcScore + chainCalcScoreLocal) of "
+                      "src/scoreChain/scoreChain.c in memory, one process per target chromosome, best of %d passes; "
+                      ".2bit unpack + chain parsing excluded (%.1f s wall incl. them)"
+                      % (n_chains, sum(o["blocks"] for o in outs), bp / 1e6, len(t_pick), len(q_pick),
+                         max(1, steps + warmup), wall),
+            "host_cores": cores, "parity_checked_jobs": checked, "parity_mismatches": mismatches,
+            "ms_per_step": sec * 1e3, "aligned_bp": bp}
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--blocks", type=int, default=10_000_000, help="job-blocks per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-mbp", type=float, default=160.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    config = {"workload": "genome-wide synthetic hg38 x mm10 chain set (BASELINE.json configs[4]): all sequences of "
+                          "example/{hg38,mm10}.chrom.sizes, %d job-blocks per GPU, default matrix, linearGap medium, "
+                          "global+local score per chain" % args.blocks,
+              "blocks_per_gpu": args.blocks, "parallelism": "independent shards x%d, full genome copy per GPU" % world,
+              "l2": "inputs (work-list + touched genome sectors, ~0.6 GB) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if not os.path.exists(REF_DRIVER):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"}))
+            return
+        w = build_workload(args.blocks, 0, plant=True)
+        res = cpu_reference(w, args.steps, args.warmup, int(args.cpu_sample_mbp * 1e6))
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from genomealignmenttools_b200 import ChainScorer, Scoring
+    from genomealignmenttools_b200.engine import PinnedArray
+    from genomealignmenttools_b200.records import JOB_DTYPE, BLOCK_DTYPE
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = build_workload(args.blocks, rank)
+    stream = torch.cuda.current_stream()
+    sc = ChainScorer(local_rank, stream=stream.cuda_stream)
+    t0 = time.time()
+    sc.load_genome("t", w.t)
+    sc.load_genome("q", w.q)
+    sc.set_scoring(Scoring(None, "medium"))
+    log("[rank %d] genomes resident in HBM after %.1f s" % (rank, time.time() - t0))
+
+    # ---- device-resident timing (value)
+    wl = sc.upload(w.jobs, w.total, w.blocks)
+    for _ in range(warmup):
+        wl.run()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        wl.run()
+    e1.record(stream)
+    barrier()
+    t_end = time.time()
+    ms = e0.elapsed_time(e1)
+    g_res, l_res = wl.results()
+    launches = sc.stats()["kernel_launches"] * args.steps
+
+    # ---- kernel-only pass for the roofline (events around the scoring kernel, same stream)
+    sc.set_profiling(True)
+    kms = []
+    for _ in range(args.steps):
+        wl.run()
+        sc.synchronize()
+        kms.append(sc.stats()["score_kernel_ms"])
+    sc.set_profiling(False)
+    kernel_ms = float(np.mean(kms))
+
+    # ---- end-to-end through the public call with pinned host buffers (e2e)
+    pj, pb = PinnedArray(len(w.jobs), JOB_DTYPE), PinnedArray(len(w.blocks), BLOCK_DTYPE)
+    pg, pl = PinnedArray(len(w.jobs), np.int64), PinnedArray(len(w.jobs), np.int64)
+    pj.array[:] = w.jobs
+    pb.array[:] = w.blocks
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e2.record(stream)
+    for _ in range(e2e_steps):
+        sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
+    e3.record(stream)
+    barrier()
+    e2e_wall_ms = (time.time() - tw0) * 1e3 / e2e_steps
+    e2e_ms = max(e2.elapsed_time(e3) / e2e_steps, e2e_wall_ms)   # the call blocks: wall time is the honest one
+    assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "e2e and resident results differ"
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+
+    per_step_ms = ms / args.steps
+    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes())],
+                         dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        per_step_ms, e2e_ms, kernel_ms = mx[0].item(), mx[1].item(), mx[2].item()
+        total_bp = sm[3].item()
+    else:
+        total_bp = float(w.aligned_bp)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = w.algorithmic_bytes() / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": total_bp / (per_step_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+            "e2e": {"value": total_bp / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": int(w.jobs.nbytes + w.blocks.nbytes), "d2h_bytes_per_step": int(16 * len(w.jobs)),
+                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "kernel": "scoreChunksKernel",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": w.algorithmic_bytes()},
+            "clocks": clocks,
+            "aligned_bp_per_gpu": w.aligned_bp, "chains_per_gpu": int(len(w.jobs)),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            t0 = time.time()
+            res = cpu_reference(w, 2, 1, int(args.cpu_sample_mbp * 1e6), gpu_scores=(g_res, l_res))
+            if res is not None:
+                line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores",
+                                                            "parity_checked_jobs", "parity_mismatches")}
+                log("cpu baseline leg took %.1f s" % (time.time() - t0))
+                if res["parity_mismatches"]:
+                    raise SystemExit("bench: %d GPU scores differ from the reference" % res["parity_mismatches"])
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref/ref_driver missing"}
+        print(json.dumps(line))
+    wl.free()
+    for p in (pj, pb, pg, pl):
+        p.free()
+    sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,506 @@
+// gat_capi.cu -- the C ABI of include/gat.h on top of the kernels in gat_kernels.cuh.
+// No CPU scoring path exists in this library: every score comes out of scoreChunksKernel.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "gat.h"
+#include "gat_kernels.cuh"
+
+using namespace gat;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(GAT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct GenomeDev {
+    uint32_t *planes = nullptr, *nplane = nullptr, *nwin = nullptr;
+    long long *seqBase = nullptr;
+    uint32_t *seqSize = nullptr;
+    uint32_t nSeq = 0;
+    bool loaded = false;
+    void release()
+    {
+        cudaFree(planes); cudaFree(nplane); cudaFree(nwin); cudaFree(seqBase); cudaFree(seqSize);
+        planes = nplane = nwin = nullptr; seqBase = nullptr; seqSize = nullptr; nSeq = 0; loaded = false;
+    }
+    GenomeView view() const { return GenomeView{planes, nplane, nwin, (const int64_t *)seqBase, seqSize, nSeq}; }
+};
+
+struct gat_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    GenomeDev genome[2];
+    // scoring
+    bool scoringSet = false, sym = false;
+    int coef[16];
+    GapView gap;
+    int *gapSmall = nullptr, *gapLongPos = nullptr;
+    double *gapLongVal = nullptr;
+    size_t dynSmem = 0;
+    int *err = nullptr;
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev[6];
+    gat_stats stats;
+};
+
+struct gat_worklist {
+    gat_job *jobs = nullptr;
+    gat_block *blocks = nullptr;
+    uint64_t nJobs = 0, totalJobBlocks = 0, nBlocks = 0;
+    uint32_t nChunks = 0;
+    uint32_t *chunkJob = nullptr;
+    Tup *chunkHead = nullptr, *chunkTail = nullptr;
+    int *chunkTailJob = nullptr;
+    long long *outGlobal = nullptr, *outLocal = nullptr;
+};
+
+extern "C" const char *gat_last_error(void) { return g_err; }
+
+extern "C" int gat_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int gat_create(gat_ctx **out, int device, void *stream)
+{
+    if (!out) return fail(GAT_EINVAL, "gat_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(GAT_ECUDA, "gat_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(GAT_EINVAL, "gat_create: device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GAT_ECUDA, "gat_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
+    gat_ctx *ctx = new gat_ctx();
+    ctx->device = device;
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->ownStream = true; }
+    CU(cudaMalloc(&ctx->err, sizeof(int)));
+    CU(cudaMemset(ctx->err, 0, sizeof(int)));
+    for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    *out = ctx;
+    return GAT_OK;
+}
+
+extern "C" void gat_destroy(gat_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->genome[0].release();
+    ctx->genome[1].release();
+    cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->err);
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, uint64_t packedBytes,
+                               const uint64_t *seqByteOffset, const uint32_t *seqSize, uint32_t nSeq,
+                               const gat_nrun *nRuns, uint64_t nNRuns)
+{
+    if (!ctx || (side != GAT_TARGET && side != GAT_QUERY)) return fail(GAT_EINVAL, "gat_load_genome: bad ctx/side");
+    if (nSeq == 0 || !seqByteOffset || !seqSize) return fail(GAT_EINVAL, "gat_load_genome: no sequences");
+    if (packedBytes && !packed) return fail(GAT_EINVAL, "gat_load_genome: packed is NULL");
+    CU(cudaSetDevice(ctx->device));
+    GenomeDev &g = ctx->genome[side];
+    g.release();
+
+    // host-side layout: every sequence starts on a 128-base group boundary
+    std::vector<long long> base(nSeq);
+    std::vector<unsigned long long> wordStart(nSeq + 1);
+    long long cursor = (long long)PAD_FRONT_GROUPS * GROUP_BASES;
+    unsigned long long words = 0;
+    for (uint32_t i = 0; i < nSeq; i++) {
+        uint64_t bytes = ((uint64_t)seqSize[i] + 3) / 4;
+        if (seqByteOffset[i] + bytes > packedBytes)
+            return fail(GAT_EINVAL, "gat_load_genome: sequence %u payload runs past packedBytes", i);
+        base[i] = cursor;
+        wordStart[i] = words;
+        words += ((unsigned long long)seqSize[i] + 31) / 32;
+        cursor += (long long)(((unsigned long long)seqSize[i] + GROUP_BASES - 1) / GROUP_BASES) * GROUP_BASES;
+    }
+    wordStart[nSeq] = words;
+    const long long totalBases = cursor + (long long)PAD_BACK_GROUPS * GROUP_BASES;
+    if ((unsigned long long)totalBases >> 5 >= 0x7fffffffull)
+        return fail(GAT_EINVAL, "gat_load_genome: genome of %lld bases exceeds the 2^36-base layout limit", totalBases);
+    const size_t planeWords = (size_t)(totalBases / GROUP_BASES) * 8;
+    const size_t nWords = (size_t)(totalBases / 32) + 2;
+    const size_t winWords = (size_t)((totalBases >> NWIN_SHIFT) / 32) + 2;
+
+    // N runs: the reference stops at the first run that starts at/after the sequence end and clips
+    // the others to it (twoBit.c:838-850)
+    std::vector<gat_nrun> runs;
+    runs.reserve(nNRuns);
+    {
+        uint32_t curSeq = 0xffffffffu;
+        bool stopped = false;
+        for (uint64_t i = 0; i < nNRuns; i++) {
+            gat_nrun r = nRuns[i];
+            if (r.seq >= nSeq) return fail(GAT_EINVAL, "gat_load_genome: N run %llu names sequence %u", (unsigned long long)i, r.seq);
+            if (r.seq != curSeq) { curSeq = r.seq; stopped = false; }
+            if (stopped) continue;
+            if (r.start >= seqSize[r.seq]) { stopped = true; continue; }
+            if ((uint64_t)r.start + r.len > seqSize[r.seq]) r.len = seqSize[r.seq] - r.start;
+            if (r.len) runs.push_back(r);
+        }
+    }
+
+    uint8_t *dRaw = nullptr;
+    unsigned long long *dByteOff = nullptr, *dWordStart = nullptr;
+    gat_nrun *dRuns = nullptr;
+    auto cleanup = [&]() { cudaFree(dRaw); cudaFree(dByteOff); cudaFree(dWordStart); cudaFree(dRuns); };
+#define CUG(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { cleanup(); g.release();                                            \
+            return fail(GAT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); }               \
+    } while (0)
+    CUG(cudaMalloc(&g.planes, planeWords * 4));
+    CUG(cudaMalloc(&g.nplane, nWords * 4));
+    CUG(cudaMalloc(&g.nwin, winWords * 4));
+    CUG(cudaMalloc(&g.seqBase, nSeq * sizeof(long long)));
+    CUG(cudaMalloc(&g.seqSize, nSeq * sizeof(uint32_t)));
+    CUG(cudaMalloc(&dRaw, packedBytes + 16));
+    CUG(cudaMalloc(&dByteOff, nSeq * sizeof(unsigned long long)));
+    CUG(cudaMalloc(&dWordStart, (nSeq + 1) * sizeof(unsigned long long)));
+    cudaStream_t st = ctx->stream;
+    CUG(cudaMemsetAsync(g.planes, 0, planeWords * 4, st));
+    CUG(cudaMemsetAsync(g.nplane, 0, nWords * 4, st));
+    CUG(cudaMemsetAsync(g.nwin, 0, winWords * 4, st));
+    CUG(cudaMemcpyAsync(dRaw, packed, packedBytes, cudaMemcpyHostToDevice, st));
+    CUG(cudaMemcpyAsync(dByteOff, seqByteOffset, nSeq * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUG(cudaMemcpyAsync(dWordStart, wordStart.data(), (nSeq + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    CUG(cudaMemcpyAsync(g.seqBase, base.data(), nSeq * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUG(cudaMemcpyAsync(g.seqSize, seqSize, nSeq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (words) {
+        unsigned long long grid = (words + 255) / 256;
+        repackKernel<<<(unsigned)grid, 256, 0, st>>>(dRaw, dByteOff, g.seqSize, g.seqBase, dWordStart, nSeq, words, g.planes);
+        CUG(cudaGetLastError());
+    }
+    if (!runs.empty()) {
+        CUG(cudaMalloc(&dRuns, runs.size() * sizeof(gat_nrun)));
+        CUG(cudaMemcpyAsync(dRuns, runs.data(), runs.size() * sizeof(gat_nrun), cudaMemcpyHostToDevice, st));
+        unsigned long long grid = (runs.size() * 32 + 255) / 256;
+        nRunKernel<<<(unsigned)grid, 256, 0, st>>>(dRuns, runs.size(), g.seqBase, g.nplane, g.nwin);
+        CUG(cudaGetLastError());
+    }
+    CUG(cudaStreamSynchronize(st));
+#undef CUG
+    cleanup();
+    g.nSeq = nSeq;
+    g.loaded = true;
+    return GAT_OK;
+}
+
+// Is M the 6-value strand-symmetric form?  (see scoreWindow<true>)
+static bool symmetricCoefs(const int32_t m[4][4], int coef[16])
+{
+    const int mTT = m[0][0], mCC = m[1][1], ts = m[0][1], tvTA = m[0][2], tvCG = m[1][3], tvX = m[0][3];
+    for (int q = 0; q < 4; q++)
+        for (int t = 0; t < 4; t++) {
+            int x1 = ((q ^ t) >> 1) & 1, x0 = (q ^ t) & 1, q0 = q & 1, want;
+            if (!x1 && !x0) want = q0 ? mCC : mTT;
+            else if (!x1) want = ts;
+            else if (!x0) want = q0 ? tvCG : tvTA;
+            else want = tvX;
+            if (m[q][t] != want) return false;
+        }
+    coef[0] = mTT;
+    coef[1] = tvTA - mTT;
+    coef[2] = ts - mTT;
+    coef[3] = tvX - tvTA - ts + mTT;
+    coef[4] = mCC - mTT;
+    coef[5] = tvCG - tvTA - mCC + mTT;
+    for (int i = 6; i < 16; i++) coef[i] = 0;
+    return true;
+}
+
+static void moebiusCoefs(const int32_t m[4][4], int coef[16])
+{   // index bits: 8=q1 4=q0 2=t1 1=t0
+    for (int q = 0; q < 4; q++)
+        for (int t = 0; t < 4; t++) coef[(q << 2) | t] = m[q][t];
+    for (int bit = 1; bit < 16; bit <<= 1)
+        for (int i = 0; i < 16; i++)
+            if (i & bit) coef[i] -= coef[i ^ bit];
+}
+
+extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
+{
+    if (!ctx || !s) return fail(GAT_EINVAL, "gat_set_scoring: NULL argument");
+    if (s->smallSize < 1 || s->smallSize > 8192 || s->longCount < 2 || s->longCount > 64)
+        return fail(GAT_EINVAL, "gat_set_scoring: smallSize %d / longCount %d outside supported range (1..8192, 2..64)",
+                    s->smallSize, s->longCount);
+    if (!s->qSmall || !s->tSmall || !s->bSmall || !s->longPos || !s->qLong || !s->tLong || !s->bLong)
+        return fail(GAT_EINVAL, "gat_set_scoring: NULL table");
+    if (s->longPos[0] != s->smallSize)
+        return fail(GAT_EINVAL, "gat_set_scoring: longPos[0] must equal smallSize (gapCalc.c:185-195)");
+    for (int i = 1; i < s->longCount; i++)
+        if (s->longPos[i] <= s->longPos[i - 1]) return fail(GAT_EINVAL, "gat_set_scoring: longPos not increasing");
+    for (int q = 0; q < 4; q++)
+        for (int t = 0; t < 4; t++)
+            if (s->matrix[q][t] > (1 << 20) || s->matrix[q][t] < -(1 << 20))
+                return fail(GAT_EINVAL, "gat_set_scoring: |matrix| above 2^20 would overflow the 32-bit window sums");
+    CU(cudaSetDevice(ctx->device));
+    ctx->sym = symmetricCoefs(s->matrix, ctx->coef);
+    if (!ctx->sym) moebiusCoefs(s->matrix, ctx->coef);
+    const int S = s->smallSize, L = s->longCount;
+    std::vector<int> small(3 * (size_t)S);
+    std::vector<double> longVal(3 * (size_t)L);
+    for (int i = 0; i < S; i++) { small[i] = s->qSmall[i]; small[S + i] = s->tSmall[i]; small[2 * S + i] = s->bSmall[i]; }
+    for (int i = 0; i < L; i++) { longVal[i] = s->qLong[i]; longVal[L + i] = s->tLong[i]; longVal[2 * L + i] = s->bLong[i]; }
+    ctx->gap.smallSize = S;
+    ctx->gap.longCount = L;
+    ctx->gap.lastPos = s->longPos[L - 1];
+    for (int w = 0; w < 3; w++) {
+        const double *v = &longVal[(size_t)w * L];
+        ctx->gap.lastVal[w] = v[L - 1];
+        // calcSlope, gapCalc.c:106-110, evaluated on the host in IEEE double like the reference
+        volatile double dy = v[L - 1] - v[L - 2];
+        volatile double dx = (double)s->longPos[L - 1] - (double)s->longPos[L - 2];
+        ctx->gap.lastSlope[w] = dy / dx;
+    }
+    cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal);
+    ctx->gapSmall = ctx->gapLongPos = nullptr; ctx->gapLongVal = nullptr;
+    CU(cudaMalloc(&ctx->gapSmall, small.size() * sizeof(int)));
+    CU(cudaMalloc(&ctx->gapLongPos, L * sizeof(int)));
+    CU(cudaMalloc(&ctx->gapLongVal, longVal.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->gapSmall, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->gapLongPos, s->longPos, L * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->gapLongVal, longVal.data(), longVal.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->dynSmem = (size_t)3 * L * sizeof(double) + (size_t)L * sizeof(int) + (size_t)3 * S * sizeof(int);
+    CU(cudaFuncSetAttribute(scoreChunksKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->dynSmem));
+    CU(cudaFuncSetAttribute(scoreChunksKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->dynSmem));
+    ctx->scoringSet = true;
+    return GAT_OK;
+}
+
+static int allocWorklist(gat_ctx *ctx, uint64_t nJobs, uint64_t totalJobBlocks, uint64_t nBlocks, gat_worklist **out)
+{
+    if (nJobs >= 0x7fffffffull || nBlocks > 0xffffffffull || totalJobBlocks > 0xffffffffull)
+        return fail(GAT_EINVAL, "work-list too large for 32-bit indices (jobs %llu, blocks %llu, job-blocks %llu)",
+                    (unsigned long long)nJobs, (unsigned long long)nBlocks, (unsigned long long)totalJobBlocks);
+    gat_worklist *wl = new gat_worklist();
+    wl->nJobs = nJobs; wl->totalJobBlocks = totalJobBlocks; wl->nBlocks = nBlocks;
+    wl->nChunks = (uint32_t)((totalJobBlocks + CHUNK - 1) / CHUNK);
+    *out = wl;
+    CU(cudaMalloc(&wl->jobs, (nJobs + 1) * sizeof(gat_job)));
+    CU(cudaMalloc(&wl->blocks, (nBlocks + 1) * sizeof(gat_block)));
+    CU(cudaMalloc(&wl->chunkJob, ((size_t)wl->nChunks + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&wl->chunkHead, ((size_t)wl->nChunks + 1) * sizeof(Tup)));
+    CU(cudaMalloc(&wl->chunkTail, ((size_t)wl->nChunks + 1) * sizeof(Tup)));
+    CU(cudaMalloc(&wl->chunkTailJob, ((size_t)wl->nChunks + 1) * sizeof(int)));
+    CU(cudaMalloc(&wl->outGlobal, (nJobs + 1) * sizeof(long long)));
+    CU(cudaMalloc(&wl->outLocal, (nJobs + 1) * sizeof(long long)));
+    return GAT_OK;
+}
+
+extern "C" void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl)
+{
+    if (!wl) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(wl->jobs); cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->chunkHead);
+    cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal);
+    delete wl;
+}
+
+static int uploadWorklist(gat_ctx *ctx, gat_worklist *wl, const gat_job *jobs, const gat_block *blocks)
+{
+    if (wl->nJobs) CU(cudaMemcpyAsync(wl->jobs, jobs, wl->nJobs * sizeof(gat_job), cudaMemcpyHostToDevice, ctx->stream));
+    if (wl->nBlocks) CU(cudaMemcpyAsync(wl->blocks, blocks, wl->nBlocks * sizeof(gat_block), cudaMemcpyHostToDevice, ctx->stream));
+    return GAT_OK;
+}
+
+extern "C" int gat_worklist_create(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint64_t totalJobBlocks,
+                                   const gat_block *blocks, uint64_t nBlocks, gat_worklist **out)
+{
+    if (!ctx || !out) return fail(GAT_EINVAL, "gat_worklist_create: NULL argument");
+    if ((nJobs && !jobs) || (nBlocks && !blocks)) return fail(GAT_EINVAL, "gat_worklist_create: NULL array");
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    gat_worklist *wl = nullptr;
+    int rc = allocWorklist(ctx, nJobs, totalJobBlocks, nBlocks, &wl);
+    if (rc == GAT_OK) rc = uploadWorklist(ctx, wl, jobs, blocks);
+    if (rc == GAT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(GAT_ECUDA, "work-list upload failed");
+    if (rc != GAT_OK) { gat_worklist_destroy(ctx, wl); return rc; }
+    *out = wl;
+    return GAT_OK;
+}
+
+extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
+{
+    if (!ctx || !wl) return fail(GAT_EINVAL, "gat_worklist_run: NULL argument");
+    if (!ctx->genome[0].loaded || !ctx->genome[1].loaded) return fail(GAT_ESTATE, "gat_worklist_run: load both genomes first");
+    if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_worklist_run: call gat_set_scoring first");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->stats.kernel_launches = 0;
+    ctx->stats.chunks = wl->nChunks;
+    if (wl->nJobs == 0) return GAT_OK;
+    if (wl->nChunks == 0) {     // every job is empty: scores are 0
+        CU(cudaMemsetAsync(wl->outGlobal, 0, wl->nJobs * sizeof(long long), st));
+        CU(cudaMemsetAsync(wl->outLocal, 0, wl->nJobs * sizeof(long long), st));
+        return GAT_OK;
+    }
+    ScoreParams P;
+    P.jobs = wl->jobs; P.blocks = wl->blocks;
+    P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
+    P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks;
+    P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
+    memcpy(P.coef, ctx->coef, sizeof P.coef);
+    P.gap = ctx->gap;
+    P.gapSmall = ctx->gapSmall; P.gapLongPos = ctx->gapLongPos; P.gapLongVal = ctx->gapLongVal;
+    P.outGlobal = wl->outGlobal; P.outLocal = wl->outLocal;
+    P.chunkHead = wl->chunkHead; P.chunkTail = wl->chunkTail; P.chunkTailJob = wl->chunkTailJob;
+    P.err = ctx->err;
+
+    const bool prof = ctx->profiling;
+    if (prof) CU(cudaEventRecord(ctx->ev[0], st));
+    {
+        unsigned grid = (unsigned)(((unsigned long long)wl->nChunks * 32 + 255) / 256);
+        chunkIndexKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->chunkJob, wl->nChunks);
+    }
+    if (prof) CU(cudaEventRecord(ctx->ev[1], st));
+    if (ctx->sym) scoreChunksKernel<true><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
+    else scoreChunksKernel<false><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
+    if (prof) CU(cudaEventRecord(ctx->ev[2], st));
+    {
+        unsigned grid = (unsigned)(((unsigned long long)wl->nChunks * 32 + 255) / 256);
+        fixupKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
+                                          wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal);
+    }
+    if (prof) CU(cudaEventRecord(ctx->ev[3], st));
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches = 3;
+    return GAT_OK;
+}
+
+static int finishStats(gat_ctx *ctx)
+{
+    if (ctx->profiling && ctx->stats.kernel_launches) {
+        CU(cudaEventSynchronize(ctx->ev[3]));
+        CU(cudaEventElapsedTime(&ctx->stats.score_kernel_ms, ctx->ev[1], ctx->ev[2]));
+        CU(cudaEventElapsedTime(&ctx->stats.all_kernels_ms, ctx->ev[0], ctx->ev[3]));
+    }
+    return GAT_OK;
+}
+
+static int checkDeviceError(gat_ctx *ctx)
+{
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, ctx->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        cudaMemsetAsync(ctx->err, 0, sizeof(int), ctx->stream);
+        return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s",
+                    (err & ERR_SEQ) ? " sequence index out of range;" : "",
+                    (err & ERR_BLOCKIDX) ? " block index out of range;" : "",
+                    (err & ERR_COORD) ? " block coordinates outside their sequence;" : "");
+    }
+    return GAT_OK;
+}
+
+extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local)
+{
+    if (!ctx || !wl) return fail(GAT_EINVAL, "gat_worklist_results: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    if (wl->nJobs) {
+        if (global) CU(cudaMemcpyAsync(global, wl->outGlobal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        if (local) CU(cudaMemcpyAsync(local, wl->outLocal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int rc = checkDeviceError(ctx);
+    if (rc != GAT_OK) return rc;
+    return finishStats(ctx);
+}
+
+extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint64_t totalJobBlocks,
+                         const gat_block *blocks, uint64_t nBlocks, int64_t *global, int64_t *local)
+{
+    if (!ctx) return fail(GAT_EINVAL, "gat_score: NULL ctx");
+    if ((nJobs && (!jobs || !global || !local)) || (nBlocks && !blocks)) return fail(GAT_EINVAL, "gat_score: NULL array");
+    if (!ctx->genome[0].loaded || !ctx->genome[1].loaded) return fail(GAT_ESTATE, "gat_score: load both genomes first");
+    if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_score: call gat_set_scoring first");
+    if (nJobs == 0) return GAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    gat_worklist *wl = nullptr;
+    int rc = allocWorklist(ctx, nJobs, totalJobBlocks, nBlocks, &wl);
+    cudaStream_t st = ctx->stream;
+    const bool prof = ctx->profiling;
+    if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[4], st);
+    if (rc == GAT_OK) rc = uploadWorklist(ctx, wl, jobs, blocks);
+    if (rc == GAT_OK) rc = gat_worklist_run(ctx, wl);
+    if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[5], st);
+    if (rc == GAT_OK) rc = gat_worklist_results(ctx, wl, global, local);
+    if (rc == GAT_OK && prof) {
+        float total = 0;
+        cudaEventElapsedTime(&total, ctx->ev[4], ctx->ev[0]);
+        ctx->stats.h2d_ms = total;
+        ctx->stats.h2d_bytes = nJobs * sizeof(gat_job) + nBlocks * sizeof(gat_block);
+        ctx->stats.d2h_bytes = 2 * nJobs * sizeof(long long);
+    }
+    gat_worklist_destroy(ctx, wl);
+    return rc;
+}
+
+extern "C" int gat_synchronize(gat_ctx *ctx)
+{
+    if (!ctx) return fail(GAT_EINVAL, "gat_synchronize: NULL ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GAT_OK;
+}
+
+extern "C" int gat_get_stats(gat_ctx *ctx, gat_stats *out)
+{
+    if (!ctx || !out) return fail(GAT_EINVAL, "gat_get_stats: NULL argument");
+    int rc = finishStats(ctx);
+    *out = ctx->stats;
+    return rc;
+}
+
+extern "C" int gat_set_profiling(gat_ctx *ctx, int on)
+{
+    if (!ctx) return fail(GAT_EINVAL, "gat_set_profiling: NULL ctx");
+    ctx->profiling = on != 0;
+    return GAT_OK;
+}
+
+extern "C" void *gat_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(GAT_ENOMEM, "gat_host_alloc: cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void gat_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}

@@ -1,0 +1,141 @@
+"""ChainScorer: the host-side handle on one GPU's scoring context (gat_ctx).
+
+Mirrors how the reference tools use the path: open the two genomes once, fix the scoring
+scheme, then score chains -- except that chains arrive as one CSR work-list per call instead of
+one chainCalcScore() call each (kent/src/lib/chainConnect.c:24)."""
+import ctypes
+import numpy as np
+from . import _native
+from .records import BLOCK_DTYPE, JOB_DTYPE, NRUN_DTYPE
+
+TARGET, QUERY = 0, 1
+
+
+class GatError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("gat error %d: %s" % (code, message))
+        self.code = code
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None and a.size else ctypes.c_void_p(0)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (gat_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        lib = _native.load()
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        self._p = lib.gat_host_alloc(max(n, 1))
+        if not self._p:
+            raise GatError(-5, lib.gat_last_error().decode())
+        buf = (ctypes.c_uint8 * max(n, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            _native.load().gat_host_free(self._p)
+            self._p = None
+            self.array = None
+
+
+class ResidentWorklist:
+    def __init__(self, scorer, handle, n_jobs):
+        self.scorer, self.handle, self.n_jobs = scorer, handle, n_jobs
+
+    def run(self):
+        self.scorer._check(self.scorer.lib.gat_worklist_run(self.scorer.ctx, self.handle))
+
+    def results(self, out_global=None, out_local=None):
+        g = np.empty(self.n_jobs, dtype=np.int64) if out_global is None else out_global
+        l = np.empty(self.n_jobs, dtype=np.int64) if out_local is None else out_local
+        self.scorer._check(self.scorer.lib.gat_worklist_results(self.scorer.ctx, self.handle, _ptr(g), _ptr(l)))
+        return g, l
+
+    def free(self):
+        if self.handle:
+            self.scorer.lib.gat_worklist_destroy(self.scorer.ctx, self.handle)
+            self.handle = None
+
+
+class ChainScorer:
+    def __init__(self, device=0, stream=None):
+        self.lib = _native.load()
+        ctx = ctypes.c_void_p()
+        rc = self.lib.gat_create(ctypes.byref(ctx), int(device), ctypes.c_void_p(stream or 0))
+        if rc != 0:
+            raise GatError(rc, self.lib.gat_last_error().decode())
+        self.ctx = ctx
+        self._keep = []
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GatError(rc, self.lib.gat_last_error().decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.gat_destroy(self.ctx)
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def load_genome(self, side, genome):
+        """side: 0/'t' target, 1/'q' query; genome: PackedGenome (payload stays packed)."""
+        side = {"t": TARGET, "q": QUERY}.get(side, side)
+        runs = np.ascontiguousarray(genome.n_runs, dtype=NRUN_DTYPE)
+        self._check(self.lib.gat_load_genome(
+            self.ctx, side, _ptr(genome.packed), genome.packed.size, _ptr(genome.byte_offsets),
+            _ptr(genome.sizes), len(genome.sizes), _ptr(runs), len(runs)))
+
+    def set_scoring(self, scoring):
+        s = _native.GatScoring()
+        m = np.ascontiguousarray(scoring.scheme.matrix, dtype=np.int32)
+        for q in range(4):
+            for t in range(4):
+                s.matrix[q][t] = int(m[q, t])
+        g = scoring.gap
+        keep = [np.ascontiguousarray(a) for a in (g.q_small, g.t_small, g.b_small, g.long_pos, g.q_long, g.t_long, g.b_long)]
+        s.smallSize = g.small_size
+        s.qSmall, s.tSmall, s.bSmall = keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data
+        s.longCount = len(g.long_pos)
+        s.longPos, s.qLong, s.tLong, s.bLong = (k.ctypes.data for k in keep[3:])
+        self._check(self.lib.gat_set_scoring(self.ctx, ctypes.byref(s)))
+
+    @staticmethod
+    def _norm(jobs, blocks):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        return jobs, blocks
+
+    def score(self, jobs, total_job_blocks, blocks, out_global=None, out_local=None):
+        """gat_score: host arrays in, (global, local) int64 arrays out."""
+        jobs, blocks = self._norm(jobs, blocks)
+        g = np.empty(len(jobs), dtype=np.int64) if out_global is None else out_global
+        l = np.empty(len(jobs), dtype=np.int64) if out_local is None else out_local
+        self._check(self.lib.gat_score(self.ctx, _ptr(jobs), len(jobs), int(total_job_blocks),
+                                       _ptr(blocks), len(blocks), _ptr(g), _ptr(l)))
+        return g, l
+
+    def upload(self, jobs, total_job_blocks, blocks):
+        jobs, blocks = self._norm(jobs, blocks)
+        h = ctypes.c_void_p()
+        self._check(self.lib.gat_worklist_create(self.ctx, _ptr(jobs), len(jobs), int(total_job_blocks),
+                                                 _ptr(blocks), len(blocks), ctypes.byref(h)))
+        return ResidentWorklist(self, h, len(jobs))
+
+    def synchronize(self):
+        self._check(self.lib.gat_synchronize(self.ctx))
+
+    def set_profiling(self, on):
+        self._check(self.lib.gat_set_profiling(self.ctx, 1 if on else 0))
+
+    def stats(self):
+        st = _native.GatStats()
+        self._check(self.lib.gat_get_stats(self.ctx, ctypes.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}

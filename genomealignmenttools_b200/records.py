@@ -1,0 +1,51 @@
+"""Work-list record layouts, byte-identical to include/gat.h (gat_block, gat_job, gat_nrun)."""
+import numpy as np
+
+BLOCK_DTYPE = np.dtype([("tStart", "<i4"), ("qStart", "<i4"), ("size", "<u4")])
+JOB_DTYPE = np.dtype([("tSeq", "<u4"), ("qSeq", "<u4"), ("firstBlock", "<u4"), ("blockPtr", "<u4"),
+                      ("clipStart", "<i4"), ("clipEnd", "<i4")])
+NRUN_DTYPE = np.dtype([("seq", "<u4"), ("start", "<u4"), ("len", "<u4")])
+assert BLOCK_DTYPE.itemsize == 12 and JOB_DTYPE.itemsize == 24 and NRUN_DTYPE.itemsize == 12
+
+QSEQ_MINUS = 0x80000000
+BLOCK_JOINED = 0x80000000
+NO_CLIP_START = -(2 ** 31)
+NO_CLIP_END = 2 ** 31 - 1
+
+
+def jobs_from_counts(t_seq, q_seq, minus, n_blocks, first_block=None, clip_start=None, clip_end=None):
+    """Build a JOB_DTYPE array from per-job columns; blockPtr is the exclusive prefix sum."""
+    n_blocks = np.asarray(n_blocks, dtype=np.int64)
+    jobs = np.zeros(len(n_blocks), dtype=JOB_DTYPE)
+    ptr = np.zeros(len(n_blocks) + 1, dtype=np.int64)
+    np.cumsum(n_blocks, out=ptr[1:])
+    jobs["tSeq"] = t_seq
+    jobs["qSeq"] = np.asarray(q_seq, dtype=np.uint32) | (np.asarray(minus, dtype=np.uint32) << np.uint32(31))
+    jobs["blockPtr"] = ptr[:-1]
+    jobs["firstBlock"] = ptr[:-1] if first_block is None else first_block
+    jobs["clipStart"] = NO_CLIP_START if clip_start is None else clip_start
+    jobs["clipEnd"] = NO_CLIP_END if clip_end is None else clip_end
+    return jobs, int(ptr[-1])
+
+
+def job_block_counts(jobs, total_job_blocks):
+    ptr = np.append(jobs["blockPtr"].astype(np.int64), np.int64(total_job_blocks))
+    return np.diff(ptr)
+
+
+def ali_bases(jobs, total_job_blocks, blocks):
+    """aliBases of chainCalcScoreLocal (src/scoreChain/scoreChain.c:180-182): the sum of clipped
+    block sizes per job.  Plain host arithmetic on the work-list, as SURVEY.md 8b prescribes."""
+    counts = job_block_counts(jobs, total_job_blocks)
+    out = np.zeros(len(jobs), dtype=np.int64)
+    if len(jobs) == 0 or counts.sum() == 0:
+        return out
+    job_of = np.repeat(np.arange(len(jobs)), counts)
+    within = np.arange(counts.sum()) - np.repeat(jobs["blockPtr"].astype(np.int64), counts)
+    idx = jobs["firstBlock"].astype(np.int64)[job_of] + within
+    ts = blocks["tStart"].astype(np.int64)[idx]
+    te = ts + (blocks["size"][idx] & np.uint32(0x7FFFFFFF)).astype(np.int64)
+    ts = np.maximum(ts, jobs["clipStart"].astype(np.int64)[job_of])
+    te = np.minimum(te, jobs["clipEnd"].astype(np.int64)[job_of])
+    np.add.at(out, job_of, te - ts)
+    return out

@@ -1,0 +1,154 @@
+/* include/gat.h -- the drop-in boundary: a C ABI for batched chain rescoring on one B200.
+ *
+ * What it replaces.  In hillerlab/GenomeAlignmentTools every chain / net fill / suspect
+ * sub-chain is scored by one synchronous CPU call
+ *     double chainCalcScore(struct chain*, struct axtScoreScheme*, struct gapCalc*,
+ *                           struct dnaSeq *query, struct dnaSeq *target)
+ *                                                   kent/src/inc/chainConnect.h:34-38
+ * (implementation kent/src/lib/chainConnect.c:14-40, gap costs kent/src/lib/gapCalc.c:298-331)
+ * plus the hillerlab addition chainCalcScoreLocal (src/scoreChain/scoreChain.c:176-198,
+ * src/chainCleaner/chainCleaner.c:531-551), reached from the tool wrappers getChainScore()
+ * at src/scoreChain/scoreChain.c:207-220, src/chainNet/chainNet.c:230-248 and
+ * src/chainCleaner/chainCleaner.c:559-571.  The host side of the tools keeps parsing
+ * .chain/.2bit/.net; instead of calling chainCalcScore per chain it builds a CSR work-list
+ * and makes ONE gat_score() call.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions.  Plain pointers and sizes only.  Every function returns 0 on success or a
+ * negative GAT_E* code; gat_last_error() describes the failure (tool wrappers turn that into
+ * kent's errAbort: message on stderr, exit(-1), kent/src/lib/errAbort.c:182-197).  There is
+ * no CPU fallback: without a CUDA device gat_create fails.  One context drives one GPU; calls on
+ * a context are serialised by the caller (the reference is single-threaded).  Scores are int64
+ * and equal, as integers, the doubles kent computes (it sums ints into a double; exact < 2^53).
+ */
+#ifndef GAT_H
+#define GAT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAT_OK 0
+#define GAT_ECUDA (-1)    /* CUDA runtime failure */
+#define GAT_EINVAL (-2)   /* bad argument */
+#define GAT_ESTATE (-3)   /* genome / scoring not loaded yet */
+#define GAT_EWORKLIST (-4)/* the device found an out-of-range record in the work-list */
+#define GAT_ENOMEM (-5)
+
+#define GAT_TARGET 0
+#define GAT_QUERY 1
+
+#define GAT_QSEQ_MINUS 0x80000000u  /* gat_job.qSeq bit: query on '-' strand (chain.h:58 qStrand) */
+#define GAT_BLOCK_JOINED 0x80000000u/* gat_block.size bit: this record continues the previous record's
+                                     * gapless block (a long block split by the host for load
+                                     * balance): no gap cost, no local-score clamp between them */
+#define GAT_NO_CLIP_START INT32_MIN
+#define GAT_NO_CLIP_END INT32_MAX
+
+/* One gapless block (struct cBlock, kent/src/inc/chain.h:17-25, minus the list pointer):
+ * target [tStart, tStart+size), query [qStart, qStart+size), 0-based half-open, per sequence;
+ * query coordinates of a '-' chain are in reverse-complement space (chainFormat.doc). */
+typedef struct gat_block {
+    int32_t tStart;
+    int32_t qStart;
+    uint32_t size;
+} gat_block;
+
+/* One scoring job = one chainCalcScore call of the reference: a chain, or the part of a chain
+ * inside a target range (chainSubsetOnT, kent/src/lib/chain.c:471-558).  Jobs form a CSR over
+ * "job-blocks": job j owns job-blocks [blockPtr[j], blockPtr[j+1]) which are the records
+ * blocks[firstBlock .. firstBlock + n).  Several jobs may point into the same records (net
+ * fills / sub-chains of one chain).  Every kept record is clipped to [clipStart, clipEnd) on
+ * the target with the query moved by the same delta (chain.c:513-522). */
+typedef struct gat_job {
+    uint32_t tSeq;       /* target sequence index (order of gat_load_genome) */
+    uint32_t qSeq;       /* query sequence index | GAT_QSEQ_MINUS */
+    uint32_t firstBlock; /* index into blocks[] */
+    uint32_t blockPtr;   /* CSR row pointer: sum of block counts of jobs 0..j-1 */
+    int32_t clipStart;   /* GAT_NO_CLIP_START when the whole chain is scored */
+    int32_t clipEnd;     /* GAT_NO_CLIP_END   "                              */
+} gat_job;
+
+/* One run of N in a sequence (nStarts/nSizes of the .2bit record, kent/src/inc/twoBit.h:9-22). */
+typedef struct gat_nrun {
+    uint32_t seq;
+    uint32_t start;
+    uint32_t len;
+} gat_nrun;
+
+/* Scoring parameters = struct axtScoreScheme's live 4x4 (kent/src/inc/axt.h:83-91; every other
+ * cell of its 256x256 matrix is 0, which is how N scores 0) + the tables struct gapCalc holds
+ * (kent/src/lib/gapCalc.c:12-37). */
+typedef struct gat_scoring {
+    int32_t matrix[4][4];   /* [query base][target base], base codes T=0 C=1 A=2 G=3 (dnautil.h:23-27) */
+    int32_t smallSize;      /* gaps < smallSize are table look-ups */
+    const int32_t *qSmall;  /* [smallSize], entry 0 is 0 */
+    const int32_t *tSmall;
+    const int32_t *bSmall;
+    int32_t longCount;      /* knots for gaps >= smallSize; longPos[0] == smallSize */
+    const int32_t *longPos; /* [longCount] */
+    const double *qLong;    /* [longCount] */
+    const double *tLong;
+    const double *bLong;
+} gat_scoring;
+
+typedef struct gat_ctx gat_ctx;
+typedef struct gat_worklist gat_worklist;
+
+/* Timing / traffic of the most recent scoring call, for bench.py and the tools' -verbose line. */
+typedef struct gat_stats {
+    float score_kernel_ms;  /* the block-scoring kernel alone (CUDA events on the ctx stream) */
+    float all_kernels_ms;   /* chunk index + scoring + cross-chunk fix-up */
+    float h2d_ms, d2h_ms;   /* 0 for resident work-lists */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t kernel_launches;
+    uint32_t chunks;        /* CTAs of the scoring kernel */
+} gat_stats;
+
+const char *gat_last_error(void);
+int gat_device_count(void);
+
+/* Context on CUDA device `device`.  `stream` is a cudaStream_t to launch on (e.g. the caller's
+ * current stream, so that its CUDA events bracket our kernels); NULL = a stream the ctx owns. */
+int gat_create(gat_ctx **out, int device, void *stream);
+void gat_destroy(gat_ctx *ctx);
+
+/* Upload one genome and keep it resident (replaces twoBitReadSeqFrag's unpack-to-chars,
+ * kent/src/lib/twoBit.c:725-878, and the whole-chromosome reverseComplement copies of
+ * scoreChain.c:123-149).  `packed` holds each sequence's .2bit payload (4 bases/byte, first
+ * base in bits 7..6) starting at byte seqByteOffset[i]; nRuns must be grouped by sequence in
+ * file order. */
+int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, uint64_t packedBytes,
+                    const uint64_t *seqByteOffset, const uint32_t *seqSize, uint32_t nSeq,
+                    const gat_nrun *nRuns, uint64_t nNRuns);
+
+int gat_set_scoring(gat_ctx *ctx, const gat_scoring *scoring);
+
+/* The hot call.  Host arrays in, host arrays out, blocking.  `totalJobBlocks` closes the CSR
+ * (= blockPtr of a virtual job nJobs).  global[j] = chainCalcScore, local[j] =
+ * chainCalcScoreLocal of job j.  (aliBases is the plain sum of clipped sizes: host arithmetic.) */
+int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint64_t totalJobBlocks,
+              const gat_block *blocks, uint64_t nBlocks, int64_t *global, int64_t *local);
+
+/* Same work split into upload / run / download, for callers that keep a work-list resident
+ * (repeated scoring with different matrices, benchmarking the kernels without PCIe). */
+int gat_worklist_create(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint64_t totalJobBlocks,
+                        const gat_block *blocks, uint64_t nBlocks, gat_worklist **out);
+int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl);           /* asynchronous on the ctx stream */
+int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local);
+void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl);
+
+int gat_synchronize(gat_ctx *ctx);
+int gat_get_stats(gat_ctx *ctx, gat_stats *out);
+/* When on, gat_worklist_run/gat_score bracket each kernel with CUDA events (filled into gat_stats). */
+int gat_set_profiling(gat_ctx *ctx, int on);
+
+/* Pinned host memory for work-lists and results (cudaHostAlloc): PCIe at full rate. */
+void *gat_host_alloc(size_t bytes);
+void gat_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

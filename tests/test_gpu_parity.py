@@ -1,0 +1,248 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the reference's golden vectors
+and the fixtures produced by the compiled reference.  Bit-exact: these are integer scores."""
+import os
+import numpy as np
+import pytest
+from genomealignmenttools_b200 import ChainScorer, Scoring, ScoreScheme, GapCalc, GatError, chainio, synth
+from genomealignmenttools_b200.twobit import PackedGenome
+from genomealignmenttools_b200.records import (JOB_DTYPE, BLOCK_DTYPE, NRUN_DTYPE, NO_CLIP_START, NO_CLIP_END,
+                                               BLOCK_JOINED, QSEQ_MINUS, ali_bases)
+import make_golden_helpers as helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_score(t, q, scoring, jobs, total, blocks):
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", t)
+        sc.load_genome("q", q)
+        sc.set_scoring(scoring)
+        return sc.score(jobs, total, blocks)
+
+
+def scoring_of(golden, matrix, gap):
+    return Scoring(ScoreScheme.read(os.path.join(golden, matrix)) if matrix else None, gap)
+
+
+@pytest.mark.parametrize("name,want", [("newStyleLastz", 671823), ("oldStyleBlastz", 671644)])
+def test_kent_axtchain_golden(golden, name, want):
+    d = os.path.join(golden, "kent_chrM")
+    t, q = PackedGenome.read_2bit(os.path.join(d, "hg19.chrM.2bit")), PackedGenome.read_2bit(os.path.join(d, "susScr3.chrM.2bit"))
+    cs = chainio.ChainSet.read(os.path.join(d, name + ".chain"))
+    jobs, total = cs.jobs(t, q)
+    g, l = gpu_score(t, q, scoring_of(golden, "kent_chrM/%s.Q.txt" % name, "loose"), jobs, total, cs.blocks)
+    assert g[0] == want == int(cs.score[0]) and l[0] == want
+
+
+def test_chrM_known_answers(golden):
+    d = os.path.join(golden, "kent_chrM")
+    t, q = PackedGenome.read_2bit(os.path.join(d, "hg19.chrM.2bit")), PackedGenome.read_2bit(os.path.join(d, "susScr3.chrM.2bit"))
+    cs = chainio.ChainSet.read(os.path.join(d, "newStyleLastz.chain"))
+    jobs, total = cs.jobs(t, q)
+    g, l = gpu_score(t, q, scoring_of(golden, "example/HoxD55.q", "loose"), jobs, total, cs.blocks)
+    assert (g[0], l[0]) == (829041, 829041)
+    g, l = gpu_score(t, q, Scoring(None, "medium"), jobs, total, cs.blocks)
+    assert (g[0], l[0]) == (767508, 767508)
+    assert ali_bases(jobs, total, cs.blocks)[0] == 15310
+
+
+@pytest.mark.parametrize("tag,matrix,gap", [
+    ("medium_default", None, "medium"), ("loose_hoxd55", "example/HoxD55.q", "loose"),
+    ("loose_lastz", "kent_chrM/newStyleLastz.Q.txt", "loose"), ("medium_asym", "synth_small/asym.q", "medium")])
+@pytest.mark.parametrize("tfile", ["t.2bit", "t.swapped.2bit"])
+def test_synth_small_reference_scorechain(golden, tag, matrix, gap, tfile):
+    d = os.path.join(golden, "synth_small")
+    t, q = PackedGenome.read_2bit(os.path.join(d, tfile)), PackedGenome.read_2bit(os.path.join(d, "q.2bit"))
+    cs = chainio.ChainSet.read(os.path.join(d, "in.chain"))
+    jobs, total = cs.jobs(t, q)
+    g, l = gpu_score(t, q, scoring_of(golden, matrix, gap), jobs, total, cs.blocks)
+    rows = np.loadtxt(os.path.join(d, "scores_%s.tsv" % tag), dtype=np.int64)
+    assert np.array_equal(g, rows[:, 1]) and np.array_equal(l, rows[:, 2])
+    assert np.array_equal(ali_bases(jobs, total, cs.blocks), rows[:, 3])
+
+
+def test_synth_small_reference_subchains(golden):
+    d = os.path.join(golden, "synth_small")
+    t, q = PackedGenome.read_2bit(os.path.join(d, "t.2bit")), PackedGenome.read_2bit(os.path.join(d, "q.2bit"))
+    cs = chainio.ChainSet.read(os.path.join(d, "in.chain"))
+    whole, _ = cs.jobs(t, q)
+    rows = np.loadtxt(os.path.join(d, "sub_medium_default.tsv"), dtype=np.int64)
+    jobs = np.zeros(len(rows), dtype=JOB_DTYPE); ptr = 0
+    for k, (ix, s, e, is_null, *_rest) in enumerate(rows):
+        fb, nb, c0, c1 = cs.subset_job(int(ix), int(s), int(e))
+        jobs[k] = (whole[ix]["tSeq"], whole[ix]["qSeq"], fb, ptr, c0, c1); ptr += nb
+    g, l = gpu_score(t, q, Scoring(None, "medium"), jobs, ptr, cs.blocks)
+    live = rows[:, 3] == 0
+    assert np.array_equal(g[live], rows[live, 4]) and np.array_equal(l[live], rows[live, 5])
+    assert np.array_equal(ali_bases(jobs, ptr, cs.blocks)[live], rows[live, 6])
+    assert np.all(g[~live] == 0) and np.all(l[~live] == 0)        # kent: NULL sub-chain
+
+
+def oracle_scores(oracle, w, t_names, q_names, matrix, gap, tmp, jobs=None, total=None):
+    paths = helpers.write_case(w, t_names, q_names, tmp)
+    jobs = w.jobs if jobs is None else jobs
+    total = w.total if total is None else total
+    return oracle.score_jobs(oracle.scoring(matrix, gap), oracle.genome(paths["t"]), oracle.genome(paths["q"]),
+                             jobs, total, w.blocks)
+
+
+CASES = [
+    # seed, n_blocks, kwargs
+    (101, 30000, dict(max_chain_blocks=20000)),                       # jobs spanning many CTAs
+    (102, 20000, dict(max_chain_blocks=3, n_fraction=0.2)),           # tiny jobs, lots of N
+    (103, 8000, dict(mean_log_len=6.5, sigma_log_len=1.5, max_len=60000, max_chain_blocks=50)),   # long blocks
+    (104, 25000, dict(mean_log_len=1.0, sigma_log_len=1.0, max_chain_blocks=2000, max_gap=3)),    # 1-10 bp blocks
+    (105, 15000, dict(minus_fraction=1.0, max_chain_blocks=700)),
+    (106, 15000, dict(minus_fraction=0.0, max_gap=2000000, gap_sigma=4.0, max_chain_blocks=100)), # huge gaps
+]
+
+
+@pytest.mark.parametrize("seed,n_blocks,kw", CASES)
+@pytest.mark.parametrize("matrix,gap", [(None, "medium"), ("example/HoxD55.q", "loose"), ("synth_small/asym.q", "loose")])
+def test_random_workloads_against_oracle(oracle, golden, tmp_path, seed, n_blocks, kw, matrix, gap):
+    t_names, q_names = ["chrA", "chrB", "s3"], ["chrX", "chrY"]
+    kw = dict(kw)
+    nf = kw.pop("n_fraction", 0.01)
+    w = synth.make_workload(t_names, [3000000, 800000, 70001], q_names, [2500000, 900003], n_blocks, seed=seed,
+                            telomere_n=700, n_fraction=nf, **kw)
+    m = os.path.join(golden, matrix) if matrix else None
+    g, l = gpu_score(w.t, w.q, scoring_of(golden, matrix, gap), w.jobs, w.total, w.blocks)
+    og, ol, oa = oracle_scores(oracle, w, t_names, q_names, m, gap, tmp_path)
+    assert np.array_equal(g, og)
+    assert np.array_equal(l, ol)
+    assert np.array_equal(ali_bases(w.jobs, w.total, w.blocks), oa)
+
+
+def small_world(seed=7, n_blocks=6000, **kw):
+    t_names, q_names = ["chrA", "chrB"], ["chrX", "chrY"]
+    w = synth.make_workload(t_names, [500000, 200000], q_names, [450000, 180000], n_blocks, seed=seed,
+                            telomere_n=400, n_fraction=0.02, **kw)
+    return w, t_names, q_names
+
+
+def test_clipped_jobs_sharing_blocks(oracle, tmp_path):
+    """chainNet / chainCleaner style: many sub-chain jobs pointing into the same chain records."""
+    w, tn, qn = small_world(max_chain_blocks=3000)
+    rng = np.random.default_rng(5)
+    counts = np.diff(np.append(w.jobs["blockPtr"].astype(np.int64), w.total))
+    jobs = []
+    ptr = 0
+    for _ in range(4000):
+        j = int(rng.integers(0, len(w.jobs)))
+        fb, nb = int(w.jobs[j]["firstBlock"]), int(counts[j])
+        b = w.blocks[fb:fb + nb]
+        lo, hi = int(b[0]["tStart"]), int(b[-1]["tStart"]) + int(b[-1]["size"])
+        s = int(rng.integers(lo - 5, hi)); e = int(rng.integers(s, hi + 5))
+        t_end = b["tStart"].astype(np.int64) + b["size"]
+        keep = np.nonzero(t_end > s)[0]
+        a = int(keep[0]) if len(keep) else nb
+        stop = np.nonzero(b["tStart"][a:] >= e)[0]
+        z = a + int(stop[0]) if len(stop) else nb
+        jobs.append((w.jobs[j]["tSeq"], w.jobs[j]["qSeq"], fb + a, ptr, s, e)); ptr += z - a
+    jobs = np.array(jobs, dtype=JOB_DTYPE)
+    g, l = gpu_score(w.t, w.q, Scoring(None, "loose"), jobs, ptr, w.blocks)
+    og, ol, oa = oracle_scores(oracle, w, tn, qn, None, "loose", tmp_path, jobs, ptr)
+    assert np.array_equal(g, og) and np.array_equal(l, ol)
+    assert np.array_equal(ali_bases(jobs, ptr, w.blocks), oa)
+
+
+def test_joined_split_blocks_equal_unsplit(oracle, tmp_path):
+    """GAT_BLOCK_JOINED: a long block cut into pieces scores exactly like the block."""
+    w, tn, qn = small_world(seed=9, n_blocks=3000, mean_log_len=6.0, sigma_log_len=1.2, max_len=40000, max_chain_blocks=40)
+    counts = np.diff(np.append(w.jobs["blockPtr"].astype(np.int64), w.total))
+    nb, nj = [], []
+    for j, job in enumerate(w.jobs):
+        start = len(nb)
+        for b in w.blocks[int(job["firstBlock"]):int(job["firstBlock"]) + int(counts[j])]:
+            off, size, first = 0, int(b["size"]), True
+            piece = 97
+            while off < size:
+                n = min(piece, size - off)
+                nb.append((int(b["tStart"]) + off, int(b["qStart"]) + off, n | (0 if first else BLOCK_JOINED)))
+                off += n; first = False; piece = piece * 3 + 1
+        nj.append((job["tSeq"], job["qSeq"], start, start, NO_CLIP_START, NO_CLIP_END))
+    blocks2 = np.array(nb, dtype=BLOCK_DTYPE); jobs2 = np.array(nj, dtype=JOB_DTYPE)
+    g1, l1 = gpu_score(w.t, w.q, Scoring(None, "medium"), w.jobs, w.total, w.blocks)
+    g2, l2 = gpu_score(w.t, w.q, Scoring(None, "medium"), jobs2, len(blocks2), blocks2)
+    og, ol, _ = oracle_scores(oracle, w, tn, qn, None, "medium", tmp_path)
+    assert np.array_equal(g1, og) and np.array_equal(l1, ol)
+    assert np.array_equal(g2, og) and np.array_equal(l2, ol)
+
+
+def test_edge_cases(oracle, tmp_path):
+    rng = np.random.default_rng(1)
+    sizes_t, sizes_q = [1000, 33, 4096], [999, 64, 5000]
+    t = PackedGenome.from_codes(["t0", "t1", "t2"], [rng.integers(0, 4, n) for n in sizes_t],
+                                n_runs=np.array([(0, 0, 3), (0, 500, 40), (0, 990, 10), (2, 31, 2)], dtype=NRUN_DTYPE))
+    q = PackedGenome.from_codes(["q0", "q1", "q2"], [rng.integers(0, 4, n) for n in sizes_q],
+                                n_runs=np.array([(0, 100, 1), (1, 0, 64), (2, 4990, 10)], dtype=NRUN_DTYPE))
+    M = QSEQ_MINUS
+    blocks = np.array([
+        (0, 0, 1000 - 1), (0, 0, 999),            # whole sequences, + and -
+        (999, 998, 1), (0, 0, 1),                 # last / first base
+        (0, 0, 33), (0, 31, 33),                  # whole t1 against q1 (all N on the query)
+        (0, 0, 32), (32, 32, 32), (64, 64, 64),   # exact word multiples
+        (1, 7, 31), (40, 47, 33), (100, 200, 0),  # odd sizes and an empty block
+        (0, 0, 4096), (0, 904, 4096),             # long block at both ends of q2
+        (5, 5, 10), (30, 20, 10), (20, 40, 10),   # out-of-order blocks (negative gaps clamp to 0)
+    ], dtype=BLOCK_DTYPE)
+    jobs = np.array([
+        (0, 0, 0, 0, NO_CLIP_START, NO_CLIP_END), (0, 0 | M, 1, 1, NO_CLIP_START, NO_CLIP_END),
+        (0, 0, 2, 2, NO_CLIP_START, NO_CLIP_END), (0, 0 | M, 3, 3, NO_CLIP_START, NO_CLIP_END),
+        (1, 1, 4, 4, NO_CLIP_START, NO_CLIP_END), (1, 1 | M, 5, 5, NO_CLIP_START, NO_CLIP_END),
+        (0, 0, 6, 6, NO_CLIP_START, NO_CLIP_END), (0, 0 | M, 6, 9, NO_CLIP_START, NO_CLIP_END),
+        (0, 0, 9, 12, NO_CLIP_START, NO_CLIP_END),
+        (0, 0, 12, 15, NO_CLIP_START, NO_CLIP_END),                      # empty job (0 blocks)
+        (2, 2, 12, 15, NO_CLIP_START, NO_CLIP_END), (2, 2 | M, 13, 16, NO_CLIP_START, NO_CLIP_END),
+        (0, 0, 14, 17, NO_CLIP_START, NO_CLIP_END), (0, 0 | M, 14, 20, 8, 35),
+        (0, 0, 6, 23, 10, 100),                                          # clip through word-multiple blocks
+    ], dtype=JOB_DTYPE)
+    total = 26
+    w = synth.Workload(t, q, jobs, total, blocks)
+    for matrix, gap in ((None, "medium"), (None, "loose")):
+        g, l = gpu_score(t, q, Scoring(None, gap), jobs, total, blocks)
+        og, ol, _ = oracle_scores(oracle, w, ["t0", "t1", "t2"], ["q0", "q1", "q2"], None, gap, tmp_path)
+        assert np.array_equal(g, og), (g, og)
+        assert np.array_equal(l, ol), (l, ol)
+    assert g[4] == 0 and g[5] == 0 and g[9] == 0      # all-N query, empty job
+
+
+def test_empty_and_invalid_worklists():
+    w, _, _ = small_world(n_blocks=500)
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(Scoring(None, "loose"))
+        g, l = sc.score(np.zeros(0, dtype=JOB_DTYPE), 0, np.zeros(0, dtype=BLOCK_DTYPE))
+        assert len(g) == 0
+        empty = np.zeros(5, dtype=JOB_DTYPE)
+        g, l = sc.score(empty, 0, w.blocks)
+        assert np.all(g == 0) and np.all(l == 0)
+        bad = w.blocks.copy(); bad["tStart"][3] = 2 ** 30
+        with pytest.raises(GatError) as e:
+            sc.score(w.jobs, w.total, bad)
+        assert e.value.code == -4
+        badj = w.jobs.copy(); badj["tSeq"][0] = 77
+        with pytest.raises(GatError):
+            sc.score(badj, w.total, w.blocks)
+        g, l = sc.score(w.jobs, w.total, w.blocks)      # the context survives a rejected work-list
+        g2, l2 = sc.score(w.jobs, w.total, w.blocks)
+        assert np.array_equal(g, g2) and np.array_equal(l, l2)
+    with ChainScorer(0) as sc:
+        with pytest.raises(GatError) as e:
+            sc.score(w.jobs, w.total, w.blocks)
+        assert e.value.code == -3
+
+
+def test_resident_worklist_matches_one_shot():
+    w, _, _ = small_world(seed=12, n_blocks=9000)
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(Scoring(None, "medium"))
+        g, l = sc.score(w.jobs, w.total, w.blocks)
+        wl = sc.upload(w.jobs, w.total, w.blocks)
+        sc.set_profiling(True)
+        for _ in range(3):
+            wl.run()
+        g2, l2 = wl.results()
+        st = sc.stats()
+        wl.free()
+    assert np.array_equal(g, g2) and np.array_equal(l, l2)
+    assert st["kernel_launches"] == 3 and st["score_kernel_ms"] > 0
