@@ -268,7 +268,10 @@ def main():
         torch.cuda.synchronize()
 
     w = build_workload(args.blocks, rank)
-    stream = torch.cuda.current_stream()
+    # our kernels launch on this torch stream, so torch's CUDA events bracket them
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     sc = ChainScorer(local_rank, stream=stream.cuda_stream)
     t0 = time.time()
     sc.load_genome("t", w.t)

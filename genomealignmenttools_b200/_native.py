@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgat.so")
+LIB_PATH = os.environ.get("GAT_LIB_PATH") or os.path.join(_HERE, "libgat.so")  # env override: kernel-variant experiments
 SYNTH_LIB_PATH = os.path.join(_HERE, "libgatsynth.so")
 
 # every symbol include/gat.h declares (tests check that the library exports all of them)

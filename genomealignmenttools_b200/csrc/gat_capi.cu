@@ -57,9 +57,11 @@ struct gat_ctx {
     bool profiling = false;
     cudaEvent_t ev[6];
     gat_stats stats;
+    gat_worklist *scratch = nullptr;   // device buffers of gat_score(), grown on demand and reused
 };
 
 struct gat_worklist {
+    uint64_t capJobs = 0, capBlocks = 0, capChunks = 0;   // allocated capacities (scratch reuse)
     gat_job *jobs = nullptr;
     gat_block *blocks = nullptr;
     uint64_t nJobs = 0, totalJobBlocks = 0, nBlocks = 0;
@@ -69,6 +71,15 @@ struct gat_worklist {
     int *chunkTailJob = nullptr;
     long long *outGlobal = nullptr, *outLocal = nullptr;
 };
+
+static void freeWorklistBuffers(gat_worklist *wl)
+{
+    cudaFree(wl->jobs); cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->chunkHead);
+    cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal);
+    wl->jobs = nullptr; wl->blocks = nullptr; wl->chunkJob = nullptr; wl->chunkHead = wl->chunkTail = nullptr;
+    wl->chunkTailJob = nullptr; wl->outGlobal = wl->outLocal = nullptr;
+    wl->capJobs = wl->capBlocks = wl->capChunks = 0;
+}
 
 extern "C" const char *gat_last_error(void) { return g_err; }
 
@@ -113,6 +124,7 @@ extern "C" void gat_destroy(gat_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->genome[0].release();
     ctx->genome[1].release();
+    if (ctx->scratch) { freeWorklistBuffers(ctx->scratch); delete ctx->scratch; }
     cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->err);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -300,32 +312,47 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
     return GAT_OK;
 }
 
-static int allocWorklist(gat_ctx *ctx, uint64_t nJobs, uint64_t totalJobBlocks, uint64_t nBlocks, gat_worklist **out)
+// Size (or re-size) a work-list's device buffers.  Buffers only ever grow, so a scratch work-list
+// that has seen the largest batch allocates nothing on later calls.
+static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_t totalJobBlocks, uint64_t nBlocks)
 {
     if (nJobs >= 0x7fffffffull || nBlocks > 0xffffffffull || totalJobBlocks > 0xffffffffull)
         return fail(GAT_EINVAL, "work-list too large for 32-bit indices (jobs %llu, blocks %llu, job-blocks %llu)",
                     (unsigned long long)nJobs, (unsigned long long)nBlocks, (unsigned long long)totalJobBlocks);
-    gat_worklist *wl = new gat_worklist();
+    const uint64_t nChunks = (totalJobBlocks + CHUNK - 1) / CHUNK;
+    if (nJobs > wl->capJobs || nBlocks > wl->capBlocks || nChunks > wl->capChunks) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        const uint64_t cj = nJobs > wl->capJobs ? nJobs + nJobs / 8 : wl->capJobs;
+        const uint64_t cb = nBlocks > wl->capBlocks ? nBlocks + nBlocks / 8 : wl->capBlocks;
+        const uint64_t cc = nChunks > wl->capChunks ? nChunks + nChunks / 8 : wl->capChunks;
+        freeWorklistBuffers(wl);
+        CU(cudaMalloc(&wl->jobs, (cj + 1) * sizeof(gat_job)));
+        CU(cudaMalloc(&wl->blocks, (cb + 1) * sizeof(gat_block)));
+        CU(cudaMalloc(&wl->chunkJob, (cc + 1) * sizeof(uint32_t)));
+        CU(cudaMalloc(&wl->chunkHead, (cc + 1) * sizeof(Tup)));
+        CU(cudaMalloc(&wl->chunkTail, (cc + 1) * sizeof(Tup)));
+        CU(cudaMalloc(&wl->chunkTailJob, (cc + 1) * sizeof(int)));
+        CU(cudaMalloc(&wl->outGlobal, (cj + 1) * sizeof(long long)));
+        CU(cudaMalloc(&wl->outLocal, (cj + 1) * sizeof(long long)));
+        wl->capJobs = cj; wl->capBlocks = cb; wl->capChunks = cc;
+    }
     wl->nJobs = nJobs; wl->totalJobBlocks = totalJobBlocks; wl->nBlocks = nBlocks;
-    wl->nChunks = (uint32_t)((totalJobBlocks + CHUNK - 1) / CHUNK);
-    *out = wl;
-    CU(cudaMalloc(&wl->jobs, (nJobs + 1) * sizeof(gat_job)));
-    CU(cudaMalloc(&wl->blocks, (nBlocks + 1) * sizeof(gat_block)));
-    CU(cudaMalloc(&wl->chunkJob, ((size_t)wl->nChunks + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&wl->chunkHead, ((size_t)wl->nChunks + 1) * sizeof(Tup)));
-    CU(cudaMalloc(&wl->chunkTail, ((size_t)wl->nChunks + 1) * sizeof(Tup)));
-    CU(cudaMalloc(&wl->chunkTailJob, ((size_t)wl->nChunks + 1) * sizeof(int)));
-    CU(cudaMalloc(&wl->outGlobal, (nJobs + 1) * sizeof(long long)));
-    CU(cudaMalloc(&wl->outLocal, (nJobs + 1) * sizeof(long long)));
+    wl->nChunks = (uint32_t)nChunks;
     return GAT_OK;
+}
+
+static int allocWorklist(gat_ctx *ctx, uint64_t nJobs, uint64_t totalJobBlocks, uint64_t nBlocks, gat_worklist **out)
+{
+    gat_worklist *wl = new gat_worklist();
+    *out = wl;
+    return shapeWorklist(ctx, wl, nJobs, totalJobBlocks, nBlocks);
 }
 
 extern "C" void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl)
 {
     if (!wl) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(wl->jobs); cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->chunkHead);
-    cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal);
+    freeWorklistBuffers(wl);
     delete wl;
 }
 
@@ -447,8 +474,9 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
     if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_score: call gat_set_scoring first");
     if (nJobs == 0) return GAT_OK;
     CU(cudaSetDevice(ctx->device));
-    gat_worklist *wl = nullptr;
-    int rc = allocWorklist(ctx, nJobs, totalJobBlocks, nBlocks, &wl);
+    if (!ctx->scratch) ctx->scratch = new gat_worklist();
+    gat_worklist *wl = ctx->scratch;
+    int rc = shapeWorklist(ctx, wl, nJobs, totalJobBlocks, nBlocks);
     cudaStream_t st = ctx->stream;
     const bool prof = ctx->profiling;
     if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[4], st);
@@ -463,7 +491,6 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
         ctx->stats.h2d_bytes = nJobs * sizeof(gat_job) + nBlocks * sizeof(gat_block);
         ctx->stats.d2h_bytes = 2 * nJobs * sizeof(long long);
     }
-    gat_worklist_destroy(ctx, wl);
     return rc;
 }
 

@@ -227,8 +227,11 @@ __global__ void chunkIndexKernel(const gat_job *__restrict__ jobs, unsigned long
 // ------------------------------------------------------------------ the scoring kernel
 struct __align__(16) StageRec { uint32_t tW, qW, n, misc; };   // misc: tSh | qSh<<5 | minus<<10 | mayN<<11
 
+#ifndef GAT_MIN_CTAS
+#define GAT_MIN_CTAS 3
+#endif
 template <bool SYM>
-__global__ void __launch_bounds__(TPB, 3)
+__global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
 scoreChunksKernel(const __grid_constant__ ScoreParams P)
 {
     __shared__ uint32_t sJob[CHUNK];            // job index + 1 of every job-block of the chunk

@@ -18,12 +18,17 @@ def chain_headers(w, t_names, q_names):
     return heads, counts
 
 
-def write_case(w, t_names, q_names, d):
+def write_genomes(w, d):
     d = str(d)
     os.makedirs(d, exist_ok=True)
     paths = {"t": os.path.join(d, "t.2bit"), "q": os.path.join(d, "q.2bit"), "chain": os.path.join(d, "in.chain")}
     w.t.write_2bit(paths["t"])
     w.q.write_2bit(paths["q"])
+    return paths
+
+
+def write_case(w, t_names, q_names, d):
+    paths = write_genomes(w, d)
     heads, counts = chain_headers(w, t_names, q_names)
     chainio.write_chains(paths["chain"], heads, w.blocks, w.jobs["firstBlock"], counts)
     return paths

@@ -79,7 +79,7 @@ def test_synth_small_reference_subchains(golden):
 
 
 def oracle_scores(oracle, w, t_names, q_names, matrix, gap, tmp, jobs=None, total=None):
-    paths = helpers.write_case(w, t_names, q_names, tmp)
+    paths = helpers.write_genomes(w, tmp)
     jobs = w.jobs if jobs is None else jobs
     total = w.total if total is None else total
     return oracle.score_jobs(oracle.scoring(matrix, gap), oracle.genome(paths["t"]), oracle.genome(paths["q"]),
