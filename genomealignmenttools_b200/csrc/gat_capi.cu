@@ -27,7 +27,8 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 struct GenomeDev {
-    uint32_t *planes = nullptr, *nplane = nullptr, *nwin = nullptr;
+    uint2 *planes = nullptr;
+    uint32_t *nplane = nullptr, *nwin = nullptr;
     long long *seqBase = nullptr;
     uint32_t *seqSize = nullptr;
     uint32_t nSeq = 0;
@@ -35,7 +36,7 @@ struct GenomeDev {
     void release()
     {
         cudaFree(planes); cudaFree(nplane); cudaFree(nwin); cudaFree(seqBase); cudaFree(seqSize);
-        planes = nplane = nwin = nullptr; seqBase = nullptr; seqSize = nullptr; nSeq = 0; loaded = false;
+        planes = nullptr; nplane = nwin = nullptr; seqBase = nullptr; seqSize = nullptr; nSeq = 0; loaded = false;
     }
     GenomeView view() const { return GenomeView{planes, nplane, nwin, (const int64_t *)seqBase, seqSize, nSeq}; }
 };
@@ -49,7 +50,7 @@ struct gat_ctx {
     bool scoringSet = false, sym = false;
     int coef[16];
     GapView gap;
-    int *gapSmall = nullptr, *gapLongPos = nullptr;
+    int *gapSmall = nullptr, *gapLongPos = nullptr, *gapDense = nullptr;
     double *gapLongVal = nullptr;
     size_t dynSmem = 0;
     int *err = nullptr;
@@ -58,6 +59,7 @@ struct gat_ctx {
     cudaEvent_t ev[6];
     gat_stats stats;
     gat_worklist *scratch = nullptr;   // device buffers of gat_score(), grown on demand and reused
+    uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
 };
 
 struct gat_worklist {
@@ -125,7 +127,7 @@ extern "C" void gat_destroy(gat_ctx *ctx)
     ctx->genome[0].release();
     ctx->genome[1].release();
     if (ctx->scratch) { freeWorklistBuffers(ctx->scratch); delete ctx->scratch; }
-    cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->err);
+    cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense); cudaFree(ctx->err);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -160,7 +162,7 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
     const long long totalBases = cursor + (long long)PAD_BACK_GROUPS * GROUP_BASES;
     if ((unsigned long long)totalBases >> 5 >= 0x7fffffffull)
         return fail(GAT_EINVAL, "gat_load_genome: genome of %lld bases exceeds the 2^36-base layout limit", totalBases);
-    const size_t planeWords = (size_t)(totalBases / GROUP_BASES) * 8;
+    const size_t planeWords = (size_t)(totalBases / 32) * 2;    // one uint2 per 32 bases
     const size_t nWords = (size_t)(totalBases / 32) + 2;
     const size_t winWords = (size_t)((totalBases >> NWIN_SHIFT) / 32) + 2;
 
@@ -275,8 +277,8 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
         if (s->longPos[i] <= s->longPos[i - 1]) return fail(GAT_EINVAL, "gat_set_scoring: longPos not increasing");
     for (int q = 0; q < 4; q++)
         for (int t = 0; t < 4; t++)
-            if (s->matrix[q][t] > (1 << 20) || s->matrix[q][t] < -(1 << 20))
-                return fail(GAT_EINVAL, "gat_set_scoring: |matrix| above 2^20 would overflow the 32-bit window sums");
+            if (s->matrix[q][t] > (1 << 19) || s->matrix[q][t] < -(1 << 19))
+                return fail(GAT_EINVAL, "gat_set_scoring: |matrix| above 2^19 would overflow the 32-bit window sums");
     CU(cudaSetDevice(ctx->device));
     ctx->sym = symmetricCoefs(s->matrix, ctx->coef);
     if (!ctx->sym) moebiusCoefs(s->matrix, ctx->coef);
@@ -296,18 +298,32 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
         volatile double dx = (double)s->longPos[L - 1] - (double)s->longPos[L - 2];
         ctx->gap.lastSlope[w] = dy / dx;
     }
-    cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal);
-    ctx->gapSmall = ctx->gapLongPos = nullptr; ctx->gapLongVal = nullptr;
+    cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense);
+    ctx->gapSmall = ctx->gapLongPos = ctx->gapDense = nullptr; ctx->gapLongVal = nullptr;
+    // dense cost table up to the last knot (capped at 4 M entries per gap kind = 48 MB)
+    ctx->gap.denseSize = ctx->gap.lastPos < (1 << 22) ? ctx->gap.lastPos : (1 << 22);
     CU(cudaMalloc(&ctx->gapSmall, small.size() * sizeof(int)));
     CU(cudaMalloc(&ctx->gapLongPos, L * sizeof(int)));
     CU(cudaMalloc(&ctx->gapLongVal, longVal.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->gapSmall, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->gapLongPos, s->longPos, L * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->gapLongVal, longVal.data(), longVal.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMalloc(&ctx->gapDense, (size_t)3 * ctx->gap.denseSize * sizeof(int)));
+    {
+        dim3 grid((unsigned)((ctx->gap.denseSize + 255) / 256), 3);
+        gapDenseKernel<<<grid, 256, 0, ctx->stream>>>(ctx->gap, ctx->gapSmall, ctx->gapLongPos, ctx->gapLongVal, ctx->gapDense);
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->dynSmem = (size_t)3 * L * sizeof(double) + (size_t)L * sizeof(int) + (size_t)3 * S * sizeof(int);
     CU(cudaFuncSetAttribute(scoreChunksKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->dynSmem));
     CU(cudaFuncSetAttribute(scoreChunksKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->dynSmem));
+    {
+        int perSm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, scoreChunksKernel<true>, TPB, ctx->dynSmem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        ctx->residentCtas = (uint32_t)(perSm > 0 ? perSm : 1) * (uint32_t)sms;
+    }
     ctx->scoringSet = true;
     return GAT_OK;
 }
@@ -398,10 +414,11 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     P.jobs = wl->jobs; P.blocks = wl->blocks;
     P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
     P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks;
+    P.prefetchChunks = ctx->residentCtas;
     P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
     memcpy(P.coef, ctx->coef, sizeof P.coef);
     P.gap = ctx->gap;
-    P.gapSmall = ctx->gapSmall; P.gapLongPos = ctx->gapLongPos; P.gapLongVal = ctx->gapLongVal;
+    P.gapSmall = ctx->gapSmall; P.gapDense = ctx->gapDense; P.gapLongPos = ctx->gapLongPos; P.gapLongVal = ctx->gapLongVal;
     P.outGlobal = wl->outGlobal; P.outLocal = wl->outLocal;
     P.chunkHead = wl->chunkHead; P.chunkTail = wl->chunkTail; P.chunkTailJob = wl->chunkTailJob;
     P.err = ctx->err;
@@ -444,10 +461,11 @@ static int checkDeviceError(gat_ctx *ctx)
     CU(cudaStreamSynchronize(ctx->stream));
     if (err) {
         cudaMemsetAsync(ctx->err, 0, sizeof(int), ctx->stream);
-        return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s",
+        return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s%s",
                     (err & ERR_SEQ) ? " sequence index out of range;" : "",
                     (err & ERR_BLOCKIDX) ? " block index out of range;" : "",
-                    (err & ERR_COORD) ? " block coordinates outside their sequence;" : "");
+                    (err & ERR_COORD) ? " block coordinates outside their sequence;" : "",
+                    (err & ERR_TOOLONG) ? " a record of 2^20 bases or more (split it with GAT_BLOCK_JOINED);" : "");
     }
     return GAT_OK;
 }
