@@ -37,23 +37,47 @@ def log(*a):
 
 
 # --------------------------------------------------------------------------- workload
-def build_workload(n_blocks, rank, plant=True):
+def build_workload(blocks_per_gpu, world=1, plant=True):
+    """The whole job for `world` GPUs: world x blocks_per_gpu job-blocks (weak scaling), generated in
+    `world` seeded parts so that N=1 is exactly part 0.  Every rank builds the identical set."""
     from genomealignmenttools_b200 import synth
     tn, ts = synth.read_chrom_sizes(os.path.join(GOLDEN, "example", "hg38.chrom.sizes"))
     qn, qs = synth.read_chrom_sizes(os.path.join(GOLDEN, "example", "mm10.chrom.sizes"))
     t0 = time.time()
     t = synth.random_genome(tn, ts, 0x5EED0001, telomere_n=10000)
     q = synth.random_genome(qn, qs, 0x5EED0002, telomere_n=10000)
-    jobs, total, blocks = synth.make_chains(ts, qs, n_blocks, seed=0x5EED0050 + rank)
-    if plant:
-        synth.plant_homology(t, q, jobs, total, blocks, 0.30, 0x5EED0060 + rank)
-    synth.sprinkle_n_runs(t, "t", jobs, blocks, 0.0005, 0x5EED0070 + rank)
-    synth.sprinkle_n_runs(q, "q", jobs, blocks, 0.0005, 0x5EED0080 + rank)
+    job_parts, block_parts, total = [], [], 0
+    for part in range(world):
+        jobs, n, blocks = synth.make_chains(ts, qs, blocks_per_gpu, seed=0x5EED0050 + part)
+        if plant:
+            synth.plant_homology(t, q, jobs, n, blocks, 0.30, 0x5EED0060 + part)
+        synth.sprinkle_n_runs(t, "t", jobs, blocks, 0.0005, 0x5EED0070 + part)
+        synth.sprinkle_n_runs(q, "q", jobs, blocks, 0.0005, 0x5EED0080 + part)
+        jobs["firstBlock"] += total
+        jobs["blockPtr"] += total
+        total += n
+        job_parts.append(jobs); block_parts.append(blocks)
+    jobs = np.concatenate(job_parts) if world > 1 else job_parts[0]
+    blocks = np.concatenate(block_parts) if world > 1 else block_parts[0]
     w = synth.Workload(t, q, jobs, total, blocks)
     w.t_names, w.q_names = tn, qn
-    log("[rank %d] workload: %d chains, %d blocks, %.1f Mbp aligned, built in %.1f s"
-        % (rank, len(jobs), total, w.aligned_bp / 1e6, time.time() - t0))
+    log("workload: %d chains, %d blocks, %.1f Mbp aligned for %d GPU(s), built in %.1f s"
+        % (len(jobs), total, w.aligned_bp / 1e6, world, time.time() - t0))
     return w
+
+
+def shard_workload(w, rank, world):
+    """This rank's share: greedy aligned-base balance over the GPUs, records compacted per shard."""
+    from genomealignmenttools_b200 import sharding, synth
+    if world == 1:
+        return w, np.arange(len(w.jobs))
+    part, _ = sharding.assign_jobs(w.jobs, w.total, w.blocks, world)
+    idx, shard, shard_total = sharding.take_shard(w.jobs, w.total, part, rank)
+    sj, sb = sharding.compact_blocks(shard, shard_total, w.blocks)
+    mine = synth.Workload(w.t, w.q, sj, shard_total, sb)
+    mine.t_names, mine.q_names = w.t_names, w.q_names
+    log("[rank %d] shard: %d chains, %d blocks, %.1f Mbp aligned" % (rank, len(sj), shard_total, mine.aligned_bp / 1e6))
+    return mine, idx
 
 
 # --------------------------------------------------------------------------- clocks
@@ -232,7 +256,7 @@ def main():
     config = {"workload": "genome-wide synthetic hg38 x mm10 chain set (BASELINE.json configs[4]): all sequences of "
                           "example/{hg38,mm10}.chrom.sizes, %d job-blocks per GPU, default matrix, linearGap medium, "
                           "global+local score per chain" % args.blocks,
-              "blocks_per_gpu": args.blocks, "parallelism": "independent shards x%d, full genome copy per GPU" % world,
+              "blocks_per_gpu": args.blocks, "parallelism": "x%d GPUs: one job of %d x blocks_per_gpu job-blocks cut by greedy aligned-base balance, full genome copy per GPU, no collective" % (world, world),
               "l2": "inputs (work-list + touched genome sectors, ~0.6 GB) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -241,7 +265,7 @@ def main():
         if not os.path.exists(REF_DRIVER):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"}))
             return
-        w = build_workload(args.blocks, 0, plant=True)
+        w = build_workload(args.blocks, 1, plant=True)
         res = cpu_reference(w, args.steps, args.warmup, int(args.cpu_sample_mbp * 1e6))
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -267,7 +291,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    w = build_workload(args.blocks, rank)
+    w, _ = shard_workload(build_workload(args.blocks, world), rank, world)
     # our kernels launch on this torch stream, so torch's CUDA events bracket them
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)

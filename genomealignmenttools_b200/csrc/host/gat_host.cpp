@@ -1,0 +1,764 @@
+// gat_host.cpp -- see gat_host.hpp.  Compiled with -ffp-contract=off: the small gap tables are
+// built with the same double arithmetic, in the same order, as kent/src/lib/gapCalc.c:82-104.
+#include "gat_host.hpp"
+#include <algorithm>
+#include <cctype>
+#include <climits>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <queue>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+
+namespace gathost {
+
+// ------------------------------------------------------------------ errAbort / verbose
+static int g_verbose = 1;
+void verboseSetLevel(int level) { g_verbose = level; }
+int verboseLevel() { return g_verbose; }
+
+void verbose(int level, const char *fmt, ...)
+{
+    if (level > g_verbose) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fflush(stderr);
+}
+
+void errAbort(const char *fmt, ...)
+{   // message + newline on stderr, exit(-1): errAbort.c:182-222
+    va_list ap;
+    va_start(ap, fmt);
+    fflush(stdout);
+    vfprintf(stderr, fmt, ap);
+    fputc('\n', stderr);
+    va_end(ap);
+    exit(-1);
+}
+
+void fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error{buf};
+}
+
+int runTool(int (*toolMain)(int, char **), int argc, char **argv)
+{
+    try {
+        return toolMain(argc, argv);
+    } catch (const Error &e) {
+        errAbort("%s", e.message.c_str());
+    }
+}
+
+// ------------------------------------------------------------------ options
+void Options::init(int *argc, char **argv, const std::vector<OptionSpec> &specs)
+{
+    auto findSpec = [&](const std::string &name, OptionType &type) {
+        for (const auto &s : specs)
+            if (name == s.name) { type = s.type; return true; }
+        if (name == "verbose") { type = OPTION_INT; return true; }      // commonOptions, options.c:23-26
+        return false;
+    };
+    int out = 1, i = 1;
+    for (; i < *argc; i++) {
+        char *arg = argv[i];
+        if (strcmp(arg, "--") == 0) { i++; break; }
+        char *eq = strchr(arg, '=');
+        bool isOption = (eq != nullptr) || arg[0] == '-';
+        if (isOption && arg[0] == '-' && (arg[1] == 0 || isspace((unsigned char)arg[1]))) isOption = false;
+        if (isOption && eq != nullptr)      // this=that counts only if everything before '=' is a word (options.c:158-170)
+            for (char *s = arg; s < eq; ++s)
+                if (*s != '_' && *s != '-' && !isalnum((unsigned char)*s)) { isOption = false; break; }
+        if (!isOption) { argv[out++] = arg; continue; }
+        const char *nameStart = arg[0] == '-' ? arg + 1 : arg;
+        std::string name = eq ? std::string(nameStart, (size_t)(eq - nameStart)) : std::string(nameStart);
+        const char *val = eq ? eq + 1 : nullptr;
+        OptionType type;
+        if (!findSpec(name, type)) fail("-%s is not a valid option", name.c_str());
+        char *end = nullptr;
+        switch (type) {
+        case OPTION_BOOLEAN:
+            if (val) fail("boolean option -%s must not have value", name.c_str());
+            break;
+        case OPTION_STRING:
+            if (!val) fail("string option -%s must have a value", name.c_str());
+            break;
+        case OPTION_INT:
+        case OPTION_LONG_LONG:
+            if (!val) fail("int option -%s must have a value", name.c_str());
+            (void)strtoll(val, &end, 10);
+            if (*val == 0 || *end != 0)
+                fail("value of -%s is not a valid %s: \"%s\"", name.c_str(), type == OPTION_INT ? "integer" : "long long", val);
+            break;
+        case OPTION_FLOAT:
+        case OPTION_DOUBLE:
+            if (!val) fail("%s option -%s must have a value", type == OPTION_FLOAT ? "float" : "double", name.c_str());
+            (void)strtod(val, &end);
+            if (*val == 0 || *end != 0)
+                fail("value of -%s is not a valid %s: \"%s\"", name.c_str(), type == OPTION_FLOAT ? "float" : "double", val);
+            break;
+        }
+        values[name] = val ? val : "on";
+    }
+    for (; i < *argc; i++) argv[out++] = argv[i];
+    *argc = out;
+    argv[out] = nullptr;
+    if (exists("verbose")) verboseSetLevel(intVal("verbose", 0));
+}
+
+const char *Options::val(const char *name, const char *dflt) const
+{
+    auto it = values.find(name);
+    return it == values.end() ? dflt : it->second.c_str();
+}
+int Options::intVal(const char *name, int dflt) const
+{
+    auto it = values.find(name);
+    return it == values.end() ? dflt : atoi(it->second.c_str());
+}
+double Options::doubleVal(const char *name, double dflt) const
+{
+    auto it = values.find(name);
+    return it == values.end() ? dflt : atof(it->second.c_str());
+}
+
+// ------------------------------------------------------------------ .2bit
+static uint32_t rd32(const uint8_t *p, bool swap)
+{
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return swap ? __builtin_bswap32(v) : v;
+}
+static uint64_t rd64(const uint8_t *p, bool swap)
+{
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return swap ? __builtin_bswap64(v) : v;
+}
+
+bool TwoBitFile::isTwoBit(const std::string &path)
+{   // twoBitIsFile, twoBit.c: endsWith(fileName, ".2bit")
+    return path.size() >= 5 && path.compare(path.size() - 5, 5, ".2bit") == 0;
+}
+
+TwoBitFile::TwoBitFile(const std::string &path) : path_(path)
+{
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) fail("Can't open %s to read: %s", path.c_str(), strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); fail("Can't stat %s", path.c_str()); }
+    imageSize_ = (size_t)st.st_size;
+    void *m = imageSize_ ? mmap(nullptr, imageSize_, PROT_READ, MAP_PRIVATE, fd, 0) : MAP_FAILED;
+    if (m != MAP_FAILED) { image_ = static_cast<uint8_t *>(m); mapped_ = true; }
+    else {
+        image_ = static_cast<uint8_t *>(malloc(imageSize_ ? imageSize_ : 1));
+        size_t got = 0;
+        while (got < imageSize_) {
+            ssize_t r = read(fd, image_ + got, imageSize_ - got);
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got != imageSize_) { close(fd); fail("%s is truncated", path.c_str()); }
+    }
+    close(fd);
+    if (imageSize_ < 16) fail("%s doesn't have a valid twoBitSig", path.c_str());
+    uint32_t sig;
+    memcpy(&sig, image_, 4);
+    bool swap;
+    if (sig == 0x1A412743u) swap = false;                 // twoBitSig, sig.h:58-62
+    else if (sig == 0x4327411Au) swap = true;
+    else fail("%s doesn't have a valid twoBitSig", path.c_str());
+    const uint32_t version = rd32(image_ + 4, swap), count = rd32(image_ + 8, swap);
+    if (version > 1) fail("Can only handle version 0 or version 1 of this file. This is version %d", (int)version);
+    size_t pos = 16;
+    std::vector<uint64_t> offsets(count);
+    seqs_.resize(count);
+    for (uint32_t i = 0; i < count; i++) {
+        if (pos + 1 > imageSize_) fail("%s is truncated", path.c_str());
+        const size_t len = image_[pos++];
+        if (pos + len + (version ? 8 : 4) > imageSize_) fail("%s is truncated", path.c_str());
+        seqs_[i].name.assign(reinterpret_cast<const char *>(image_ + pos), len);
+        pos += len;
+        if (version == 1) { offsets[i] = rd64(image_ + pos, swap); pos += 8; }
+        else { offsets[i] = rd32(image_ + pos, swap); pos += 4; }
+        index_[seqs_[i].name] = (int)i;
+    }
+    for (uint32_t i = 0; i < count; i++) {
+        TwoBitSeq &s = seqs_[i];
+        size_t p = (size_t)offsets[i];
+        auto need = [&](size_t n) { if (p + n > imageSize_) fail("%s is truncated", path.c_str()); };
+        need(8);
+        s.size = rd32(image_ + p, swap); p += 4;
+        const uint32_t nc = rd32(image_ + p, swap); p += 4;
+        need((size_t)nc * 8 + 4);
+        s.nStart.resize(nc); s.nLen.resize(nc);
+        for (uint32_t k = 0; k < nc; k++) s.nStart[k] = rd32(image_ + p + 4 * (size_t)k, swap);
+        p += 4 * (size_t)nc;
+        for (uint32_t k = 0; k < nc; k++) s.nLen[k] = rd32(image_ + p + 4 * (size_t)k, swap);
+        p += 4 * (size_t)nc;
+        const uint32_t mc = rd32(image_ + p, swap); p += 4;
+        need((size_t)mc * 8 + 4);
+        s.maskStart.resize(mc); s.maskLen.resize(mc);
+        for (uint32_t k = 0; k < mc; k++) s.maskStart[k] = rd32(image_ + p + 4 * (size_t)k, swap);
+        p += 4 * (size_t)mc;
+        for (uint32_t k = 0; k < mc; k++) s.maskLen[k] = rd32(image_ + p + 4 * (size_t)k, swap);
+        p += 4 * (size_t)mc;
+        p += 4;     // reserved
+        need(((size_t)s.size + 3) / 4);
+        s.packed = image_ + p;
+    }
+}
+
+TwoBitFile::~TwoBitFile()
+{
+    if (mapped_) munmap(image_, imageSize_);
+    else free(image_);
+}
+
+int TwoBitFile::find(const std::string &name) const
+{
+    auto it = index_.find(name);
+    return it == index_.end() ? -1 : it->second;
+}
+
+void uploadGenome(gat_ctx *ctx, int side, const TwoBitFile &tb, const std::vector<int> &use)
+{
+    std::vector<uint64_t> offs(use.size());
+    std::vector<uint32_t> sizes(use.size());
+    std::vector<gat_nrun> runs;
+    uint64_t total = 0;
+    for (size_t i = 0; i < use.size(); i++) {
+        const TwoBitSeq &s = tb.seqs()[use[i]];
+        offs[i] = total;
+        sizes[i] = s.size;
+        total += ((uint64_t)s.size + 3) / 4;
+        for (size_t k = 0; k < s.nStart.size(); k++) runs.push_back(gat_nrun{(uint32_t)i, s.nStart[k], s.nLen[k]});
+    }
+    // the C ABI wants one buffer: gather the used payloads (pinned, so the H2D copy runs at PCIe rate)
+    uint8_t *staging = static_cast<uint8_t *>(gat_host_alloc(total ? total : 1));
+    if (!staging) fail("%s", gat_last_error());
+    for (size_t i = 0; i < use.size(); i++) {
+        const TwoBitSeq &s = tb.seqs()[use[i]];
+        memcpy(staging + offs[i], s.packed, ((size_t)s.size + 3) / 4);
+    }
+    const int rc = gat_load_genome(ctx, side, staging, total, offs.data(), sizes.data(), (uint32_t)use.size(), runs.data(), runs.size());
+    gat_host_free(staging);
+    if (rc != GAT_OK) fail("%s", gat_last_error());
+}
+
+// ------------------------------------------------------------------ text helpers
+static std::string slurp(const std::string &path)
+{
+    std::string cmd;
+    FILE *f;
+    const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
+    if (gz) {       // linefile.c:40-53: compressed files are read through a decompressor child
+        cmd = "gzip -dc '" + path + "'";
+        if (access(path.c_str(), R_OK) != 0) fail("Couldn't open %s , %s", path.c_str(), strerror(errno));
+        f = popen(cmd.c_str(), "r");
+    } else
+        f = (path == "stdin") ? stdin : fopen(path.c_str(), "rb");
+    if (!f) fail("Couldn't open %s , %s", path.c_str(), strerror(errno));
+    std::string text;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    if (gz) pclose(f);
+    else if (f != stdin) fclose(f);
+    return text;
+}
+
+// splits text into lines in place (replaces '\n' by 0); no copy
+struct LineCursor {
+    std::string &text;
+    size_t pos = 0;
+    int lineIx = 0;
+    explicit LineCursor(std::string &t) : text(t) {}
+    char *next()
+    {
+        if (pos >= text.size()) return nullptr;
+        char *line = &text[pos];
+        size_t nl = text.find('\n', pos);
+        if (nl == std::string::npos) pos = text.size();
+        else { text[nl] = 0; pos = nl + 1; }
+        lineIx++;
+        return line;
+    }
+};
+
+static int chop(char *line, char **words, int maxWords)
+{   // chopByWhite
+    int n = 0;
+    char *s = line;
+    for (;;) {
+        while (*s && isspace((unsigned char)*s)) s++;
+        if (!*s || n == maxWords) break;
+        words[n++] = s;
+        while (*s && !isspace((unsigned char)*s)) s++;
+        if (!*s) break;
+        *s++ = 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ score scheme
+ScoreScheme ScoreScheme::defaultScheme()
+{
+    static const int acgt[4][4] = {{91, -114, -31, -123}, {-114, 100, -125, -31}, {-31, -125, 100, -114}, {-123, -31, -114, 91}};
+    static const int code[4] = {2, 1, 3, 0};    // A C G T (file order) -> kent codes
+    ScoreScheme ss;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) ss.matrix[code[i]][code[j]] = acgt[i][j];
+    return ss;
+}
+
+ScoreScheme ScoreScheme::read(const std::string &path)
+{
+    static const int code[4] = {2, 1, 3, 0};
+    std::string text = slurp(path);
+    LineCursor lc(text);
+    char *w[6];
+    auto chopNext = [&](int &n) -> bool {      // lineFileChopNext, linefile.c:907-922
+        for (char *line; (line = lc.next()) != nullptr;) {
+            if (line[0] == '#') continue;
+            n = chop(line, w, 6);
+            if (n) return true;
+        }
+        return false;
+    };
+    int n;
+    for (;;) {
+        if (!chopNext(n)) fail("Scoring matrix file %s too short\n", path.c_str());
+        if (strchr(w[0], '=') || (n > 1 && strchr(w[1], '='))) continue;        // lastz settings lines
+        if (n < 4 || w[0][0] != 'A' || w[1][0] != 'C' || w[2][0] != 'G' || w[3][0] != 'T')
+            fail("%s doesn't seem to be a score matrix file", path.c_str());
+        break;
+    }
+    ScoreScheme ss;
+    for (int i = 0; i < 4; i++) {
+        if (!chopNext(n)) fail("Scoring matrix file %s too short\n", path.c_str());
+        const int first = (n == 5) ? 1 : 0;
+        if (n < first + 4) fail("Expecting 4 numbers line %d of %s", lc.lineIx, path.c_str());
+        for (int j = 0; j < 4; j++) {
+            const char *a = w[first + j];
+            if (a[0] != '-' && !isdigit((unsigned char)a[0]))
+                fail("Expecting number field %d line %d of %s, got %s", first + j + 1, lc.lineIx, path.c_str(), a);
+            ss.matrix[code[i]][code[j]] = atoi(a);
+        }
+    }
+    if (char *line = lc.next()) {       // the very next raw line must carry O= and E= (axt.c:785-805)
+        bool gotO = false, gotE = false;
+        std::vector<char *> parts;
+        for (char *p = strtok(line, " =,\t"); p; p = strtok(nullptr, " =,\t")) parts.push_back(p);
+        for (size_t i = 0; i + 1 < parts.size(); i += 2) {
+            if (strcmp(parts[i], "O") == 0) { gotO = true; ss.gapOpen = atoi(parts[i + 1]); }
+            if (strcmp(parts[i], "E") == 0) { gotE = true; ss.gapExtend = atoi(parts[i + 1]); }
+        }
+        if (!gotO || !gotE) fail("Expecting O = and E = in last line of %s", path.c_str());
+        if (ss.gapOpen <= 0 || ss.gapExtend <= 0) fail("Must have positive gap scores");
+    }
+    return ss;
+}
+
+// ------------------------------------------------------------------ gap costs
+static const char *looseCosts =
+    "tablesize       11\n"
+    "smallSize       111\n"
+    "position        1       2       3       11      111     2111    12111   32111   72111   152111  252111\n"
+    "qGap    325     360     400     450     600     1100    3600    7600    15600   31600   56600\n"
+    "tGap    325     360     400     450     600     1100    3600    7600    15600   31600   56600\n"
+    "bothGap 625     660     700     750     900     1400    4000    8000    16000   32000   57000\n";
+static const char *mediumCosts =
+    "tableSize 11\n"
+    "smallSize 111\n"
+    "position 1 2 3 11 111 2111 12111 32111 72111 152111 252111\n"
+    "qGap 350 425 450 600 900 2900 22900 57900 117900 217900 317900\n"
+    "tGap 350 425 450 600 900 2900 22900 57900 117900 217900 317900\n"
+    "bothGap 750 825 850 1000 1300 3300 23300 58300 118300 218300 318300\n";
+
+const char *GapCalc::sampleFileContents() { return looseCosts; }
+
+static int truncToInt(double d)
+{   // (int)double on x86-64: toward zero, INT_MIN when out of range
+    if (!(d > -2147483649.0 && d < 2147483648.0)) return INT_MIN;
+    return (int)d;
+}
+
+static int interpolate(int x, const std::vector<int> &s, const std::vector<double> &v)
+{   // gapCalc.c:82-104
+    const int n = (int)s.size();
+    for (int i = 0; i < n; i++) {
+        if (x == s[i]) return truncToInt(v[i]);
+        if (x < s[i]) {
+            const int ds = s[i] - s[i - 1];
+            const double dv = v[i] - v[i - 1];
+            const double prod = dv * (double)(x - s[i - 1]);
+            return truncToInt(v[i - 1] + prod / (double)ds);
+        }
+    }
+    const int ds = s[n - 1] - s[n - 2];
+    const double dv = v[n - 1] - v[n - 2];
+    const double prod = dv * (double)(x - s[n - 2]);
+    return truncToInt(v[n - 2] + prod / (double)ds);
+}
+
+GapCalc GapCalc::fromString(const std::string &spec)
+{   // gapCalcRead, gapCalc.c:146-222
+    std::string text = spec;
+    LineCursor lc(text);
+    auto tagged = [&](const char *tag, int count, std::vector<int> *iOut, std::vector<double> *dOut) {
+        char *line;
+        for (;;) {      // lineFileNextReal: skip blank lines and lines whose first non-space is '#'
+            line = lc.next();
+            if (!line) fail("Unexpected end of file in gap cost specification");
+            char *s = line;
+            while (*s && isspace((unsigned char)*s)) s++;
+            if (*s && *s != '#') break;
+        }
+        std::vector<char *> words(count + 3);
+        const int n = chop(line, words.data(), count + 2);
+        if (n == 0 || strcasecmp(words[0], tag) != 0) fail("Expecting %s got %s line %d of gap costs", tag, n ? words[0] : "", lc.lineIx);
+        if (n - 1 < count) fail("Not enough numbers line %d of gap costs", lc.lineIx);
+        if (n - 1 > count) fail("Too many numbers line %d of gap costs", lc.lineIx);
+        for (int i = 0; i < count; i++) {
+            if (!isdigit((unsigned char)words[i + 1][0])) fail("Expecting number got %s line %d of gap costs", words[i + 1], lc.lineIx);
+            if (iOut) iOut->push_back(atoi(words[i + 1]));
+            if (dOut) dOut->push_back(atof(words[i + 1]));
+        }
+    };
+    GapCalc g;
+    std::vector<int> one, pos;
+    std::vector<double> qv, tv, bv;
+    tagged("tableSize", 1, &one, nullptr);
+    const int tableSize = one[0];
+    one.clear();
+    tagged("smallSize", 1, &one, nullptr);
+    g.smallSize = one[0];
+    if (tableSize < 2 || g.smallSize < 1) fail("bad tableSize/smallSize in gap costs");
+    tagged("position", tableSize, &pos, nullptr);
+    tagged("qGap", tableSize, nullptr, &qv);
+    tagged("tGap", tableSize, nullptr, &tv);
+    tagged("bothGap", tableSize, nullptr, &bv);
+    if (pos[0] > 1) fail("gap cost positions must start at 1");
+    g.qSmall.assign(g.smallSize, 0); g.tSmall.assign(g.smallSize, 0); g.bSmall.assign(g.smallSize, 0);
+    for (int i = 1; i < g.smallSize; i++) {
+        g.qSmall[i] = interpolate(i, pos, qv);
+        g.tSmall[i] = interpolate(i, pos, tv);
+        g.bSmall[i] = interpolate(i, pos, bv);
+    }
+    int startLong = -1;
+    for (int i = 0; i < tableSize; i++)
+        if (pos[i] == g.smallSize) { startLong = i; break; }
+    if (startLong < 0) fail("No position %d in gapCalcRead()\n", g.smallSize);
+    g.longPos.assign(pos.begin() + startLong, pos.end());
+    g.qLong.assign(qv.begin() + startLong, qv.end());
+    g.tLong.assign(tv.begin() + startLong, tv.end());
+    g.bLong.assign(bv.begin() + startLong, bv.end());
+    if (g.longPos.size() < 2) fail("gap costs need at least two positions from smallSize on");
+    return g;
+}
+
+GapCalc GapCalc::fromFile(const char *name)
+{
+    if (name == nullptr) fail("Must specify linear gap costs.  Use 'loose' or 'medium' for defaults\n");
+    if (strcmp(name, "loose") == 0) { verbose(2, "using loose linear gap costs (chicken/human)\n"); return fromString(looseCosts); }
+    if (strcmp(name, "medium") == 0) { verbose(2, "using medium (original) linear gap costs (mouse/human)\n"); return fromString(mediumCosts); }
+    return fromString(slurp(name));
+}
+
+int GapCalc::cost(int dq, int dt) const
+{   // gapCalcCost, gapCalc.c:298-331
+    if (dt < 0) dt = 0;
+    if (dq < 0) dq = 0;
+    const std::vector<int32_t> *small;
+    const std::vector<double> *lng;
+    int v;
+    if (dt == 0) { small = &qSmall; lng = &qLong; v = dq; }
+    else if (dq == 0) { small = &tSmall; lng = &tLong; v = dt; }
+    else { small = &bSmall; lng = &bLong; v = (int)((unsigned)dq + (unsigned)dt); }
+    if (v < smallSize) return (*small)[v];
+    const int L = (int)longPos.size(), last = longPos[L - 1];
+    if (v >= last) {
+        const double slope = ((*lng)[L - 1] - (*lng)[L - 2]) / ((double)last - (double)longPos[L - 2]);
+        const double ext = slope * (double)(v - last);
+        return truncToInt((*lng)[L - 1] + ext);
+    }
+    return interpolate(v, std::vector<int>(longPos.begin(), longPos.end()), *lng);
+}
+
+void setScoring(gat_ctx *ctx, const ScoreScheme &ss, const GapCalc &gc)
+{
+    gat_scoring s;
+    memcpy(s.matrix, ss.matrix, sizeof s.matrix);
+    s.smallSize = gc.smallSize;
+    s.qSmall = gc.qSmall.data(); s.tSmall = gc.tSmall.data(); s.bSmall = gc.bSmall.data();
+    s.longCount = (int)gc.longPos.size();
+    s.longPos = gc.longPos.data();
+    s.qLong = gc.qLong.data(); s.tLong = gc.tLong.data(); s.bLong = gc.bLong.data();
+    if (gat_set_scoring(ctx, &s) != GAT_OK) fail("%s", gat_last_error());
+}
+
+// ------------------------------------------------------------------ chains
+static inline bool parseInt(const char *w, int &out)
+{   // lineFileNeedNum: first char '-' or digit, then atoi
+    if (w[0] != '-' && !(w[0] >= '0' && w[0] <= '9')) return false;
+    out = atoi(w);
+    return true;
+}
+
+void readChains(const std::string &path, ChainSet &out)
+{   // chainRead, chain.c:256-346
+    std::string text = slurp(path);
+    LineCursor lc(text);
+    char *w[16];
+    int nextId = 1;
+    const char *fn = path.c_str();
+    auto chopNext = [&](int maxWords) -> int {
+        for (char *line; (line = lc.next()) != nullptr;) {
+            if (line[0] == '#') { out.metaLines.emplace_back(line); continue; }
+            const int n = chop(line, w, maxWords);
+            if (n) return n;
+        }
+        return 0;
+    };
+    for (;;) {
+        int n = chopNext(13);
+        if (n == 0) break;
+        if (n < 12) fail("Expecting at least 12 words line %d of %s", lc.lineIx, fn);
+        if (strcmp(w[0], "chain") != 0) fail("Expecting 'chain' line %d of %s", lc.lineIx, fn);
+        ChainHead c;
+        c.score = atof(w[1]);
+        c.tName = w[2];
+        c.qName = w[7];
+        c.qStrand = w[9][0];
+        auto need = [&](int ix, int &v) {
+            if (!parseInt(w[ix], v)) fail("Expecting number field %d line %d of %s, got %s", ix + 1, lc.lineIx, fn, w[ix]);
+        };
+        need(3, c.tSize);
+        if (n >= 13) need(12, c.id);
+        else c.id = nextId++;
+        need(5, c.tStart); need(6, c.tEnd); need(8, c.qSize); need(10, c.qStart); need(11, c.qEnd);
+        if (c.qStart >= c.qEnd || c.tStart >= c.tEnd) fail("End before start line %d of %s", lc.lineIx, fn);
+        if (c.qStart < 0 || c.tStart < 0) fail("Start before zero line %d of %s", lc.lineIx, fn);
+        if (c.qEnd > c.qSize || c.tEnd > c.tSize) fail("Past end of sequence line %d of %s", lc.lineIx, fn);
+        c.firstBlock = out.blocks.size();
+        int q = c.qStart, t = c.tStart;
+        for (;;) {
+            n = chopNext(3);
+            if (n == 0) fail("Unexpected end of file in %s", fn);
+            int size, dt, dq;
+            if (!parseInt(w[0], size)) fail("Expecting number field 1 line %d of %s, got %s", lc.lineIx, fn, w[0]);
+            out.blocks.push_back(gat_block{t, q, (uint32_t)size});
+            t += size; q += size;
+            if (n == 1) break;
+            if (n < 3) fail("Expecting 1 or 3 words line %d of %s\n", lc.lineIx, fn);
+            if (!parseInt(w[1], dt)) fail("Expecting number field 2 line %d of %s, got %s", lc.lineIx, fn, w[1]);
+            if (!parseInt(w[2], dq)) fail("Expecting number field 3 line %d of %s, got %s", lc.lineIx, fn, w[2]);
+            t += dt; q += dq;
+        }
+        c.nBlocks = out.blocks.size() - c.firstBlock;
+        if (q != c.qEnd) fail("q end mismatch %d vs %d line %d of %s\n", q, c.qEnd, lc.lineIx, fn);
+        if (t != c.tEnd) fail("t end mismatch %d vs %d line %d of %s\n", t, c.tEnd, lc.lineIx, fn);
+        out.chains.push_back(std::move(c));
+    }
+}
+
+void writeChain(FILE *f, const ChainHead &c, const gat_block *blocks)
+{   // chainWriteHead + chainWrite, chain.c:200-227
+    fprintf(f, "chain %1.0f %s %d + %d %d %s %d %c %d %d %d\n", c.score, c.tName.c_str(), c.tSize, c.tStart, c.tEnd,
+            c.qName.c_str(), c.qSize, c.qStrand, c.qStart, c.qEnd, c.id);
+    const gat_block *b = blocks + c.firstBlock;
+    for (uint64_t i = 0; i < c.nBlocks; i++) {
+        fprintf(f, "%d", (int)b[i].size);
+        if (i + 1 < c.nBlocks)
+            fprintf(f, "\t%d\t%d", b[i + 1].tStart - (b[i].tStart + (int)b[i].size), b[i + 1].qStart - (b[i].qStart + (int)b[i].size));
+        fputc('\n', f);
+    }
+    fputc('\n', f);
+}
+
+// ------------------------------------------------------------------ work-list
+void buildRecords(const ChainSet &cs, WorkList &wl)
+{
+    wl.blocks.clear();
+    wl.blocks.reserve(cs.blocks.size());
+    wl.chainFirstRecord.assign(cs.chains.size() + 1, 0);
+    const uint32_t maxPiece = GAT_MAX_BLOCK_BASES;
+    for (size_t c = 0; c < cs.chains.size(); c++) {
+        wl.chainFirstRecord[c] = wl.blocks.size();
+        const ChainHead &h = cs.chains[c];
+        for (uint64_t i = 0; i < h.nBlocks; i++) {
+            const gat_block &b = cs.blocks[h.firstBlock + i];
+            if (b.size <= maxPiece) { wl.blocks.push_back(b); continue; }
+            // a gapless block too long for one device record: JOINED pieces score exactly like the block
+            for (uint32_t off = 0; off < b.size; off += maxPiece) {
+                const uint32_t n = std::min(maxPiece, b.size - off);
+                wl.blocks.push_back(gat_block{b.tStart + (int)off, b.qStart + (int)off, n | (off ? GAT_BLOCK_JOINED : 0u)});
+            }
+        }
+    }
+    wl.chainFirstRecord[cs.chains.size()] = wl.blocks.size();
+    if (wl.blocks.size() > 0xffffffffull) fail("more than 2^32 block records in one batch");
+}
+
+static void pushJob(WorkList &wl, uint32_t tSeq, uint32_t qSeq, char strand, uint64_t firstRecord, uint64_t nRecords,
+                    int clipStart, int clipEnd, int64_t ali)
+{
+    if (wl.totalJobBlocks + nRecords > 0xffffffffull) fail("more than 2^32 job-blocks in one batch");
+    gat_job j;
+    j.tSeq = tSeq;
+    j.qSeq = qSeq | (strand == '-' ? GAT_QSEQ_MINUS : 0u);
+    j.firstBlock = (uint32_t)firstRecord;
+    j.blockPtr = (uint32_t)wl.totalJobBlocks;
+    j.clipStart = clipStart;
+    j.clipEnd = clipEnd;
+    wl.jobs.push_back(j);
+    wl.aliBases.push_back(ali);
+    wl.totalJobBlocks += nRecords;
+}
+
+void addChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, WorkList &wl)
+{
+    const ChainHead &h = cs.chains[c];
+    int64_t ali = 0;
+    for (uint64_t i = 0; i < h.nBlocks; i++) ali += (int)cs.blocks[h.firstBlock + i].size;
+    pushJob(wl, tSeq, qSeq, h.qStrand, wl.chainFirstRecord[c], wl.chainFirstRecord[c + 1] - wl.chainFirstRecord[c],
+            GAT_NO_CLIP_START, GAT_NO_CLIP_END, ali);
+}
+
+bool addSubChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, int subStart, int subEnd, WorkList &wl)
+{   // chainSubsetOnT + chainFastSubsetOnT, chain.c:471-558
+    const ChainHead &h = cs.chains[c];
+    if (subStart <= h.tStart && subEnd >= h.tEnd) {     // the chain itself, unclipped (:501-506)
+        addChainJob(cs, c, tSeq, qSeq, wl);
+        return true;
+    }
+    const gat_block *b = cs.blocks.data() + h.firstBlock;
+    uint64_t a = 0;
+    while (a < h.nBlocks && b[a].tStart + (int)b[a].size <= subStart) a++;       // first block with tEnd > subStart (:479-484)
+    uint64_t e = a;
+    int64_t ali = 0;
+    while (e < h.nBlocks && b[e].tStart < subEnd) {                               // stop at tStart >= subEnd (:510)
+        const int ts = std::max(b[e].tStart, subStart), te = std::min(b[e].tStart + (int)b[e].size, subEnd);
+        ali += te - ts;
+        e++;
+    }
+    if (e == a) return false;
+    // map file blocks [a, e) to device records: identical unless an earlier block of the chain was split
+    uint64_t ra = wl.chainFirstRecord[c], re;
+    if (wl.chainFirstRecord[c + 1] - wl.chainFirstRecord[c] == h.nBlocks) { ra += a; re = wl.chainFirstRecord[c] + e; }
+    else {
+        auto pieces = [&](uint64_t i) { return (uint64_t)((b[i].size + GAT_MAX_BLOCK_BASES - 1) / GAT_MAX_BLOCK_BASES) + (b[i].size == 0); };
+        for (uint64_t i = 0; i < a; i++) ra += pieces(i);
+        re = ra;
+        for (uint64_t i = a; i < e; i++) re += pieces(i);
+    }
+    pushJob(wl, tSeq, qSeq, h.qStrand, ra, re - ra, subStart, subEnd, ali);
+    return true;
+}
+
+std::vector<std::vector<uint32_t>> shardJobs(const WorkList &wl, int parts)
+{
+    std::vector<std::vector<uint32_t>> out(parts);
+    if (parts <= 1) {
+        out[0].resize(wl.jobs.size());
+        for (size_t i = 0; i < wl.jobs.size(); i++) out[0][i] = (uint32_t)i;
+        return out;
+    }
+    // weight = aligned bases + a per-record term (short blocks cost more per base than long ones)
+    std::vector<uint32_t> order(wl.jobs.size());
+    std::vector<int64_t> weight(wl.jobs.size());
+    for (size_t i = 0; i < wl.jobs.size(); i++) {
+        order[i] = (uint32_t)i;
+        const uint64_t next = i + 1 < wl.jobs.size() ? wl.jobs[i + 1].blockPtr : wl.totalJobBlocks;
+        weight[i] = std::max<int64_t>(wl.aliBases[i], 0) + 64 * (int64_t)(next - wl.jobs[i].blockPtr) + 64;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+    typedef std::pair<int64_t, int> Load;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int p = 0; p < parts; p++) heap.push(Load(0, p));
+    for (uint32_t j : order) {
+        Load l = heap.top();
+        heap.pop();
+        out[l.second].push_back(j);
+        heap.push(Load(l.first + weight[j], l.second));
+    }
+    for (auto &v : out) std::sort(v.begin(), v.end());      // keep file order inside a shard: neighbours share sectors
+    return out;
+}
+
+void extractShard(const WorkList &wl, const std::vector<uint32_t> &jobIx, std::vector<gat_job> &jobs, uint64_t &total)
+{
+    jobs.resize(jobIx.size());
+    total = 0;
+    for (size_t k = 0; k < jobIx.size(); k++) {
+        const uint32_t i = jobIx[k];
+        const uint64_t next = (size_t)i + 1 < wl.jobs.size() ? wl.jobs[i + 1].blockPtr : wl.totalJobBlocks;
+        jobs[k] = wl.jobs[i];
+        jobs[k].blockPtr = (uint32_t)total;
+        total += next - wl.jobs[i].blockPtr;
+    }
+}
+
+MultiGpu::MultiGpu(int nGpus)
+{
+    const int have = gat_device_count();
+    if (have == 0) fail("no CUDA device: chain scoring has no CPU path (%s)", gat_last_error());
+    if (nGpus > have) fail("-gpus=%d but only %d CUDA device(s) visible", nGpus, have);
+    for (int d = 0; d < nGpus; d++) {
+        gat_ctx *c = nullptr;
+        if (gat_create(&c, d, nullptr) != GAT_OK) fail("%s", gat_last_error());
+        ctx.push_back(c);
+    }
+}
+
+MultiGpu::~MultiGpu()
+{
+    for (gat_ctx *c : ctx) gat_destroy(c);
+}
+
+void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local)
+{
+    global.assign(wl.jobs.size(), 0);
+    local.assign(wl.jobs.size(), 0);
+    if (wl.jobs.empty()) return;
+    if (ctx.size() == 1) {
+        if (gat_score(ctx[0], wl.jobs.data(), wl.jobs.size(), wl.totalJobBlocks, wl.blocks.data(), wl.blocks.size(),
+                      global.data(), local.data()) != GAT_OK)
+            fail("%s", gat_last_error());
+        return;
+    }
+    // one host thread per GPU; every GPU holds a full genome copy, shards are independent (no collective)
+    const auto shards = shardJobs(wl, (int)ctx.size());
+    std::vector<std::string> errors(ctx.size());
+    std::vector<std::thread> threads;
+    for (size_t g = 0; g < ctx.size(); g++)
+        threads.emplace_back([&, g]() {
+            std::vector<gat_job> jobs;
+            uint64_t total = 0;
+            extractShard(wl, shards[g], jobs, total);
+            std::vector<int64_t> gl(jobs.size()), lo(jobs.size());
+            if (!jobs.empty() &&
+                gat_score(ctx[g], jobs.data(), jobs.size(), total, wl.blocks.data(), wl.blocks.size(), gl.data(), lo.data()) != GAT_OK) {
+                errors[g] = gat_last_error();
+                return;
+            }
+            for (size_t k = 0; k < jobs.size(); k++) { global[shards[g][k]] = gl[k]; local[shards[g][k]] = lo[k]; }
+        });
+    for (auto &t : threads) t.join();
+    for (const auto &e : errors)
+        if (!e.empty()) fail("%s", e.c_str());
+}
+
+}  // namespace gathost

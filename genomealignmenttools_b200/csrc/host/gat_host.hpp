@@ -1,0 +1,136 @@
+// gat_host.hpp -- host side of the chain tools: everything between the files on disk and the
+// batched C ABI of include/gat.h.  It mirrors the pieces of kent the three hillerlab tools use
+// around chainCalcScore -- option parsing (lib/options.c), errAbort (lib/errAbort.c), the .2bit
+// container (lib/twoBit.c), score schemes (lib/axt.c), gap tables (lib/gapCalc.c), .chain I/O
+// and chainSubsetOnT (lib/chain.c) -- with the same file formats, messages and exit codes, but
+// its output is a CSR work-list for the GPU instead of per-chain CPU calls.  No scoring here.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "gat.h"
+
+namespace gathost {
+
+// ---- errAbort / verbose (kent/src/lib/errAbort.c:182-222, verbose.c:19-31)
+[[noreturn]] void errAbort(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void verbose(int level, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+void verboseSetLevel(int level);
+int verboseLevel();
+// Library code throws; tools call runTool() which turns an Error into errAbort.
+struct Error { std::string message; };
+[[noreturn]] void fail(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+int runTool(int (*toolMain)(int, char **), int argc, char **argv);
+
+// ---- options (kent/src/lib/options.c:41-203, 306)
+enum OptionType { OPTION_BOOLEAN, OPTION_STRING, OPTION_INT, OPTION_FLOAT, OPTION_DOUBLE, OPTION_LONG_LONG };
+struct OptionSpec { const char *name; OptionType type; };
+class Options {
+public:
+    // Removes the option words from argv (like optionInit) and validates them against specs
+    // (+ the common -verbose=N).  "--" stops option parsing.
+    void init(int *argc, char **argv, const std::vector<OptionSpec> &specs);
+    bool exists(const char *name) const { return values.count(name) != 0; }
+    const char *val(const char *name, const char *dflt) const;
+    int intVal(const char *name, int dflt) const;
+    double doubleVal(const char *name, double dflt) const;
+private:
+    std::map<std::string, std::string> values;
+};
+
+// ---- .2bit container (kent/src/lib/twoBit.c:422-513, 574-650); the payload stays packed
+struct TwoBitSeq {
+    std::string name;
+    uint32_t size = 0;
+    const uint8_t *packed = nullptr;              // (size+3)/4 bytes inside the file image
+    std::vector<uint32_t> nStart, nLen, maskStart, maskLen;
+};
+class TwoBitFile {
+public:
+    static bool isTwoBit(const std::string &path);           // twoBitIsFile: name ends in .2bit
+    explicit TwoBitFile(const std::string &path);
+    ~TwoBitFile();
+    TwoBitFile(const TwoBitFile &) = delete;
+    TwoBitFile &operator=(const TwoBitFile &) = delete;
+    int find(const std::string &name) const;                 // -1 if absent
+    const std::vector<TwoBitSeq> &seqs() const { return seqs_; }
+    const std::string &path() const { return path_; }
+private:
+    std::string path_;
+    uint8_t *image_ = nullptr;
+    size_t imageSize_ = 0;
+    bool mapped_ = false;
+    std::vector<TwoBitSeq> seqs_;
+    std::unordered_map<std::string, int> index_;
+};
+
+// Upload the sequences `use` (indices into tb.seqs(), in that order) with gat_load_genome.
+void uploadGenome(gat_ctx *ctx, int side, const TwoBitFile &tb, const std::vector<int> &use);
+
+// ---- scoring parameters
+struct ScoreScheme {                               // struct axtScoreScheme, kent/src/inc/axt.h:83-91
+    int32_t matrix[4][4];                          // [q][t], kent codes T=0 C=1 A=2 G=3
+    int gapOpen = 400, gapExtend = 30;
+    static ScoreScheme defaultScheme();            // axtScoreSchemeDefault, axt.c:423-458
+    static ScoreScheme read(const std::string &path);   // axtScoreSchemeRead, axt.c:692-834
+};
+struct GapCalc {                                   // struct gapCalc, kent/src/lib/gapCalc.c:12-37
+    int smallSize = 0;
+    std::vector<int32_t> qSmall, tSmall, bSmall, longPos;
+    std::vector<double> qLong, tLong, bLong;
+    static GapCalc fromFile(const char *name);     // gapCalcFromFile: "loose", "medium" or a file
+    static GapCalc fromString(const std::string &text);
+    static const char *sampleFileContents();       // gapCalcSampleFileContents, gapCalc.c:75-79
+    int cost(int dq, int dt) const;                // gapCalcCost (host restatement for -verbose paths / tests)
+};
+void setScoring(gat_ctx *ctx, const ScoreScheme &ss, const GapCalc &gc);
+
+// ---- chains (kent/src/inc/chain.h:48-63, lib/chain.c:200-346, 471-558)
+struct ChainHead {
+    double score = 0;
+    std::string tName, qName;
+    int tSize = 0, tStart = 0, tEnd = 0, qSize = 0, qStart = 0, qEnd = 0, id = 0;
+    char qStrand = '+';
+    uint64_t firstBlock = 0, nBlocks = 0;          // into ChainSet::blocks
+};
+struct ChainSet {
+    std::vector<ChainHead> chains;
+    std::vector<gat_block> blocks;                 // exactly the blocks of the file (never split)
+    std::vector<std::string> metaLines;            // '#' lines (chainNet / chainCleaner pass them through)
+};
+// Reads every chain of a file (plain, or .gz through `gzip -dc` like linefile.c:40-53).
+void readChains(const std::string &path, ChainSet &out);
+void writeChain(FILE *f, const ChainHead &c, const gat_block *blocks);     // chainWrite, chain.c:211-227
+
+// ---- work-list
+struct WorkList {
+    std::vector<gat_job> jobs;
+    std::vector<gat_block> blocks;                 // device records: long blocks split into JOINED pieces
+    uint64_t totalJobBlocks = 0;
+    std::vector<uint64_t> chainFirstRecord;        // first device record of every chain (+ sentinel)
+    std::vector<int64_t> aliBases;                 // per job: sum of clipped sizes (scoreChain.c:182)
+};
+// Device records for all chains of a set; tSeq/qSeq come from the name->index maps.
+void buildRecords(const ChainSet &cs, WorkList &wl);
+// One whole-chain job (what scoreChain scores).
+void addChainJob(const ChainSet &cs, size_t chainIx, uint32_t tSeq, uint32_t qSeq, WorkList &wl);
+// chainSubsetOnT (chain.c:471-558) as a job; returns false for kent's NULL sub-chain (no job added).
+bool addSubChainJob(const ChainSet &cs, size_t chainIx, uint32_t tSeq, uint32_t qSeq, int subStart, int subEnd, WorkList &wl);
+// Greedy longest-processing-time split of jobs over `parts` GPUs by aligned bases.
+std::vector<std::vector<uint32_t>> shardJobs(const WorkList &wl, int parts);
+// Sub-work-list holding the given jobs (block records are shared, so only jobs are re-indexed).
+void extractShard(const WorkList &wl, const std::vector<uint32_t> &jobIx, std::vector<gat_job> &jobs, uint64_t &totalJobBlocks);
+
+// Score a work-list on `nGpus` devices (each with its own context, genomes already loaded by
+// `prepare(ctx)`); results land in global/local indexed like wl.jobs.
+struct MultiGpu {
+    std::vector<gat_ctx *> ctx;
+    explicit MultiGpu(int nGpus);
+    ~MultiGpu();
+    void score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local);
+};
+
+}  // namespace gathost

@@ -97,6 +97,12 @@ def make_synth_small():
     run([os.path.join(REFBIN, "scoreChain"), os.path.join(d, "in.chain"), os.path.join(d, "t.2bit"),
          os.path.join(d, "q.2bit"), os.path.join(d, "scores_medium_asym.tsv"), "-returnOnlyScore",
          "-linearGap=medium", "-scoreScheme=" + os.path.join(d, "asym.q")])
+    # the other output modes of the tool, byte for byte
+    for tag, opts in (("chain_medium", ["-linearGap=medium"]), ("chain_medium_doLocal", ["-linearGap=medium", "-doLocalScore"]),
+                      ("chain_loose_forceLocal", ["-linearGap=loose", "-forceLocalScore"]),
+                      ("coords_medium", ["-linearGap=medium", "-returnOnlyScoreAndCoords"])):
+        run([os.path.join(REFBIN, "scoreChain"), os.path.join(d, "in.chain"), os.path.join(d, "t.2bit"),
+             os.path.join(d, "q.2bit"), os.path.join(d, "out_%s.txt" % tag)] + opts)
     # sub-chain (clip) answers straight from chainSubsetOnT + chainCalcScore + chainCalcScoreLocal
     ref = oracle_lib.load_ref()
     ref.set_scoring(None, "medium")
