@@ -526,7 +526,7 @@ void readChains(const std::string &path, ChainSet &out)
     const char *fn = path.c_str();
     auto chopNext = [&](int maxWords) -> int {
         for (char *line; (line = lc.next()) != nullptr;) {
-            if (line[0] == '#') { out.metaLines.emplace_back(line); continue; }
+            if (line[0] == '#') { out.metaLines.emplace_back(line); out.metaLineChain.push_back(out.chains.size()); continue; }
             const int n = chop(line, w, maxWords);
             if (n) return n;
         }

@@ -100,6 +100,7 @@ struct ChainSet {
     std::vector<ChainHead> chains;
     std::vector<gat_block> blocks;                 // exactly the blocks of the file (never split)
     std::vector<std::string> metaLines;            // '#' lines (chainNet / chainCleaner pass them through)
+    std::vector<size_t> metaLineChain;             // how many chains had been read when the line was met
 };
 // Reads every chain of a file (plain, or .gz through `gzip -dc` like linefile.c:40-53).
 void readChains(const std::string &path, ChainSet &out);

@@ -134,6 +134,12 @@ def make_synth_small():
          "-tNibDir=" + os.path.join(d, "t.2bit"), "-qNibDir=" + os.path.join(d, "q.2bit"),
          os.path.join(d, "sorted.chain"), os.path.join(d, "t.sizes"), os.path.join(d, "q.sizes"),
          os.path.join(d, "expected.t.net"), os.path.join(d, "expected.q.net")])
+    # the same net without -rescore (approximate sub-scores): pure host logic, checkable without a GPU
+    run([os.path.join(REFBIN, "chainNet"), "-minSpace=5", "-minScore=0", os.path.join(d, "sorted.chain"),
+         os.path.join(d, "t.sizes"), os.path.join(d, "q.sizes"),
+         os.path.join(d, "expected_plain.t.net"), os.path.join(d, "expected_plain.q.net")])
+    run([os.path.join(REFBIN, "chainNet"), os.path.join(d, "sorted.chain"), os.path.join(d, "t.sizes"), os.path.join(d, "q.sizes"),
+         os.path.join(d, "expected_default.t.net"), os.path.join(d, "expected_default.q.net")])
 
 
 def make_gap_kat():
