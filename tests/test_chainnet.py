@@ -36,7 +36,7 @@ def test_usage_and_errors(golden, tmp_path):
     assert r.returncode == 255 and "you must specify the target genome file" in r.stderr
     r = run(EXE, args + ["-rescore", "-tNibDir=x.2bit", "-qNibDir=y.2bit"])
     assert r.returncode == 255 and r.stderr.startswith("Must specify linear gap costs")
-    r = run(EXE, [os.path.join(d, "in.chain")] + args[1:])         # unsorted input
+    r = run(EXE, ["-minScore=0", os.path.join(d, "out_chain_loose_forceLocal.txt")] + args[1:])         # unsorted input
     assert r.returncode == 255 and "must be sorted in order of score" in r.stderr
     r = run(EXE, [args[0], args[2], args[1]] + args[3:])           # sizes swapped
     assert r.returncode == 255 and ("not found" in r.stderr or " but " in r.stderr)
