@@ -82,6 +82,34 @@ __device__ __forceinline__ Tup tupShfl(const Tup &t, int src)
     return Tup{shfl64(t.d, src), shfl64(t.c, src), shfl64(t.e, src), shfl64(t.f, src)};
 }
 
+// The same tuple in 32 bits, used by a warp whose 128 blocks are provably small enough
+// (sum of |block score| + gap cost below 2^28): a third of the instructions of the 64-bit form.
+template <typename T> struct TupT { T d, c, e, f; };
+template <typename T> __device__ __forceinline__ T negInf();
+template <> __device__ __forceinline__ long long negInf<long long>() { return NEG; }
+template <> __device__ __forceinline__ int negInf<int>() { return -(1 << 30); }
+template <typename T> __device__ __forceinline__ T maxT(T a, T b) { return a > b ? a : b; }
+template <typename T> __device__ __forceinline__ TupT<T> tIdentity() { return TupT<T>{0, negInf<T>(), negInf<T>(), negInf<T>()}; }
+template <typename T> __device__ __forceinline__ TupT<T> tCombine(const TupT<T> &x, const TupT<T> &y)
+{
+    TupT<T> r;
+    r.d = x.d + y.d;
+    r.c = maxT<T>(y.c, x.c + y.d);
+    r.e = maxT<T>(x.e, x.d + y.e);
+    r.f = maxT<T>(maxT<T>(x.f, y.f), x.c + y.e);
+    return r;
+}
+__device__ __forceinline__ int shflT(int v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ long long shflT(long long v, int src) { return shfl64(v, src); }
+template <typename T> __device__ __forceinline__ TupT<T> tShfl(const TupT<T> &t, int src)
+{
+    return TupT<T>{shflT(t.d, src), shflT(t.c, src), shflT(t.e, src), shflT(t.f, src)};
+}
+// to the 64-bit tuple that crosses warps / CTAs; anything at or below -2^29 is "minus infinity"
+__device__ __forceinline__ long long widen(long long v) { return v; }
+__device__ __forceinline__ long long widen(int v) { return v < -(1 << 29) ? NEG : (long long)v; }
+template <typename T> __device__ __forceinline__ Tup tWiden(const TupT<T> &t) { return Tup{(long long)t.d, widen(t.c), widen(t.e), widen(t.f)}; }
+
 struct GapView {           // tables of struct gapCalc (gapCalc.c:12-37) as the device sees them
     int smallSize, longCount, lastPos;
     int denseSize;                     // gapDense[which][v] holds gapCalcCost for every v < denseSize
@@ -295,6 +323,80 @@ __device__ __forceinline__ gat_block loadBlock(const gat_block *__restrict__ blo
     gat_block r;
     r.tStart = (int)__ldg(p); r.qStart = (int)__ldg(p + 1); r.size = __ldg(p + 2);
     return r;
+}
+
+// Phase 3 of scoreChunksKernel for one warp (see there), in 32- or 64-bit tuples.
+template <typename T>
+__device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const long long *sScore, const int *sGap,
+                                              const unsigned char *sFlag, const uint32_t *sJob, int warpV0,
+                                              unsigned long long vb0, unsigned long long chunkEnd, int warp, int lane,
+                                              Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead, int *sWarpPendJob,
+                                              int *sLastIsEnd, uint32_t *sLastJob)
+{
+    const T NEGT = negInf<T>();
+    TupT<T> cur = tIdentity<T>();     // open segment at the end of my run
+    bool runHasHead = false;
+    bool pend = false;                // an END reached before any HEAD of my run: needs the carry
+    TupT<T> pendTup = tIdentity<T>();
+    uint32_t pendJob = 0;
+    {
+        const int o0 = 4 * lane;
+        int p = padIdx(warpV0 + o0);
+#pragma unroll
+        for (int k = 0; k < 4; k++, p++) {
+            const unsigned char fl = sFlag[p];
+            if (fl & 8) {
+                const T a = (T)sScore[p];
+                const bool isEnd = fl & 2, joinedNext = fl & 4;
+                T dY = a, cY = NEGT;
+                if (!isEnd && !joinedNext) { dY = a - (T)sGap[p]; cY = 0; }
+                if (fl & 1) { cur = tIdentity<T>(); runHasHead = true; }
+                // cur = cur (+) element, specialised for a single block (its f is -inf)
+                TupT<T> r;
+                r.d = cur.d + dY;
+                r.c = maxT<T>(cY, cur.c + dY);
+                r.e = joinedNext ? cur.e : maxT<T>(cur.e, cur.d + a);
+                r.f = joinedNext ? cur.f : maxT<T>(cur.f, cur.c + a);
+                cur = r;
+                if (isEnd) {
+                    const uint32_t job = sJob[p] - 1;
+                    if (runHasHead) {   // job lies inside my run: done
+                        P.outGlobal[job] = (long long)cur.d;
+                        P.outLocal[job] = max64(0, max64(widen(cur.e), widen(cur.f)));
+                    } else { pend = true; pendTup = cur; pendJob = job; }
+                }
+                if (vb0 + (unsigned long long)(warpV0 + o0 + k) + 1 == chunkEnd) {
+                    *sLastIsEnd = isEnd;                // the chunk's last valid job-block
+                    *sLastJob = sJob[p] - 1;
+                }
+            }
+        }
+    }
+    // warp-level segmented inclusive scan of (cur, runHasHead)
+    TupT<T> inc = cur;
+    bool incHead = runHasHead;
+    for (int off = 1; off < 32; off <<= 1) {
+        TupT<T> o = tShfl<T>(inc, lane >= off ? lane - off : lane);
+        bool oh = __shfl_sync(FULL, (int)incHead, lane >= off ? lane - off : lane);
+        if (lane >= off && !incHead) { inc = tCombine<T>(o, inc); incHead = oh; }
+    }
+    TupT<T> carry = tShfl<T>(inc, lane ? lane - 1 : 0);
+    bool carryHead = __shfl_sync(FULL, (int)incHead, lane ? lane - 1 : 0);
+    if (lane == 0) { carry = tIdentity<T>(); carryHead = false; }
+    if (pend) {
+        const TupT<T> fin = tCombine<T>(carry, pendTup);
+        if (carryHead) {            // the job started inside this warp
+            P.outGlobal[pendJob] = (long long)fin.d;
+            P.outLocal[pendJob] = max64(0, max64(widen(fin.e), widen(fin.f)));
+        } else {                    // it started before this warp: at most one such lane per warp
+            sWarpPend[warp] = tWiden<T>(fin); sWarpPendJob[warp] = (int)pendJob;
+        }
+    }
+    const bool anyCross = __any_sync(FULL, pend && !carryHead);
+    if (lane == 31) {
+        sWarpAgg[warp] = tWiden<T>(inc); sWarpHead[warp] = incHead;
+        if (!anyCross) sWarpPendJob[warp] = -1;
+    }
 }
 
 template <bool SYM>
@@ -560,68 +662,23 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     // ---- phase 3: ordered segmented reduction of tuples, per warp: lane l walks job-blocks 4l..4l+3
     // of the warp, one warp scan joins the lanes; what crosses warps is resolved by whichever warp
     // of the CTA finishes last (no CTA-wide barrier: warps retire at their own pace).
-    Tup cur = tupIdentity();      // open segment at the end of my run
-    bool runHasHead = false;
-    bool pend = false;            // an END reached before any HEAD of my run: needs the carry
-    Tup pendTup = tupIdentity();
-    uint32_t pendJob = 0;
     {
-        const int o0 = 4 * lane;
-        int p = padIdx(warpV0 + o0);
+        // 32-bit tuples if every partial sum of this warp's blocks stays below 2^28
+        long long mag = 0;
+        const int p0 = padIdx(warpV0 + 4 * lane);
 #pragma unroll
-        for (int k = 0; k < 4; k++, p++) {
-            const unsigned char fl = sFlag[p];
-            if (fl & 8) {
-                const long long a = sScore[p] + sAcc[warp][o0 + k];
-                const bool isEnd = fl & 2, joinedNext = fl & 4;
-                long long dY = a, cY = NEG;
-                if (!isEnd && !joinedNext) { dY = a - sGap[p]; cY = 0; }
-                if (fl & 1) { cur = tupIdentity(); runHasHead = true; }
-                // cur = cur (+) element, specialised for a single block (its f is -inf)
-                Tup r;
-                r.d = cur.d + dY;
-                r.c = max64(cY, cur.c + dY);
-                r.e = joinedNext ? cur.e : max64(cur.e, cur.d + a);
-                r.f = joinedNext ? cur.f : max64(cur.f, cur.c + a);
-                cur = r;
-                if (isEnd) {
-                    const uint32_t job = sJob[p] - 1;
-                    if (runHasHead) {   // job lies inside my run: done
-                        P.outGlobal[job] = cur.d;
-                        P.outLocal[job] = max64(0, max64(cur.e, cur.f));
-                    } else { pend = true; pendTup = cur; pendJob = job; }
-                }
-                if (vb0 + (unsigned long long)(warpV0 + o0 + k) + 1 == (total < vb0 + CHUNK ? total : vb0 + CHUNK)) {
-                    sLastIsEnd = isEnd;                 // the chunk's last valid job-block
-                    sLastJob = sJob[p] - 1;
-                }
-            }
+        for (int k = 0; k < 4; k++) {
+            const long long a = sScore[p0 + k] + sAcc[warp][4 * lane + k];
+            sScore[p0 + k] = a;
+            const long long g = sGap[p0 + k];
+            mag += (a < 0 ? -a : a) + (g < 0 ? -g : g);
         }
-    }
-    // warp-level segmented inclusive scan of (cur, runHasHead)
-    Tup inc = cur;
-    bool incHead = runHasHead;
-    for (int off = 1; off < 32; off <<= 1) {
-        Tup o = tupShfl(inc, lane >= off ? lane - off : lane);
-        bool oh = __shfl_sync(FULL, (int)incHead, lane >= off ? lane - off : lane);
-        if (lane >= off && !incHead) { inc = tupCombine(o, inc); incHead = oh; }
-    }
-    Tup carry = tupShfl(inc, lane ? lane - 1 : 0);
-    bool carryHead = __shfl_sync(FULL, (int)incHead, lane ? lane - 1 : 0);
-    if (lane == 0) { carry = tupIdentity(); carryHead = false; }
-    if (pend) {
-        const Tup fin = tupCombine(carry, pendTup);
-        if (carryHead) {            // the job started inside this warp
-            P.outGlobal[pendJob] = fin.d;
-            P.outLocal[pendJob] = max64(0, max64(fin.e, fin.f));
-        } else {                    // it started before this warp: at most one such lane per warp
-            sWarpPend[warp] = fin; sWarpPendJob[warp] = (int)pendJob;
-        }
-    }
-    const bool anyCross = __any_sync(FULL, pend && !carryHead);
-    if (lane == 31) {
-        sWarpAgg[warp] = inc; sWarpHead[warp] = incHead;
-        if (!anyCross) sWarpPendJob[warp] = -1;
+        const bool small = __all_sync(FULL, mag < (1LL << 23));
+        const unsigned long long chunkEnd = total < vb0 + CHUNK ? total : vb0 + CHUNK;
+        if (small) warpJobReduce<int>(P, sScore, sGap, sFlag, sJob, warpV0, vb0, chunkEnd, warp, lane,
+                                      sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
+        else warpJobReduce<long long>(P, sScore, sGap, sFlag, sJob, warpV0, vb0, chunkEnd, warp, lane,
+                                      sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
     }
     // last warp of the CTA to get here stitches the warps together
     __threadfence_block();
