@@ -154,6 +154,11 @@ bool TwoBitFile::isTwoBit(const std::string &path)
 
 TwoBitFile::TwoBitFile(const std::string &path) : path_(path)
 {
+    struct stat pathStat;
+    if (!isTwoBit(path) && stat(path.c_str(), &pathStat) == 0 && S_ISDIR(pathStat.st_mode)) {
+        nibDir_ = true;             // a directory of .nib files; sequences are loaded when asked for
+        return;
+    }
     int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) fail("Can't open %s to read: %s", path.c_str(), strerror(errno));
     struct stat st;
@@ -229,7 +234,44 @@ TwoBitFile::~TwoBitFile()
 int TwoBitFile::find(const std::string &name) const
 {
     auto it = index_.find(name);
-    return it == index_.end() ? -1 : it->second;
+    if (it != index_.end()) return it->second;
+    return nibDir_ ? loadNib(name) : -1;
+}
+
+int TwoBitFile::loadNib(const std::string &name) const
+{   // nibOpenVerify + nibInput, kent/src/lib/nib.c:83-235
+    const std::string fileName = path_ + "/" + name + ".nib";
+    FILE *f = fopen(fileName.c_str(), "rb");
+    if (!f) fail("Can't open %s to read: %s", fileName.c_str(), strerror(errno));
+    uint32_t head[2];
+    if (fread(head, 4, 2, f) != 2) { fclose(f); fail("%s is not a good .nib file.", fileName.c_str()); }
+    uint32_t sig = head[0], size = head[1];
+    if (sig != 0x6BE93D3Au) {       // nibSig, sig.h:49; byte-swapped files are accepted
+        sig = __builtin_bswap32(sig); size = __builtin_bswap32(size);
+        if (sig != 0x6BE93D3Au) { fclose(f); fail("%s is not a good .nib file.", fileName.c_str()); }
+    }
+    std::vector<uint8_t> nib(((size_t)size + 1) / 2);
+    if (fread(nib.data(), 1, nib.size(), f) != nib.size()) { fclose(f); fail("Read error 2 in %s", fileName.c_str()); }
+    fclose(f);
+    TwoBitSeq s;
+    s.name = name;
+    s.size = size;
+    std::vector<uint8_t> packed(((size_t)size + 3) / 4, 0);
+    bool inN = false;
+    for (uint32_t i = 0; i < size; i++) {
+        const unsigned v = (i & 1) ? (nib[i >> 1] & 0xf) : (nib[i >> 1] >> 4);      // first base in the high nibble
+        const unsigned code = v & 7;                // bit 3 is the soft-mask flag: irrelevant to scores (axt.c:402-421)
+        const bool isN = code >= 4;                 // N (and the undefined codes 5..7) have all-zero matrix rows
+        if (!isN) packed[i >> 2] |= (uint8_t)(code << (6 - 2 * (i & 3)));
+        if (isN && !inN) { s.nStart.push_back(i); s.nLen.push_back(0); }
+        if (isN) s.nLen.back()++;
+        inN = isN;
+    }
+    nibPayload_.push_back(std::move(packed));
+    s.packed = nibPayload_.back().data();
+    seqs_.push_back(std::move(s));
+    index_[name] = (int)seqs_.size() - 1;
+    return (int)seqs_.size() - 1;
 }
 
 void uploadGenome(gat_ctx *ctx, int side, const TwoBitFile &tb, const std::vector<int> &use)

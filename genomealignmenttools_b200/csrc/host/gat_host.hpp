@@ -51,11 +51,15 @@ struct TwoBitSeq {
 class TwoBitFile {
 public:
     static bool isTwoBit(const std::string &path);           // twoBitIsFile: name ends in .2bit
+    // A .2bit file, or -- what chainNet / chainCleaner also accept as tNibDir / qNibDir
+    // (chainNet.c:166-170) -- a directory of <name>.nib files (kent/src/lib/nib.c:83-235: 4 bits
+    // per base, T=0 C=1 A=2 G=3 N=4, bit 3 = soft-masked).  A nib sequence is converted to the
+    // .2bit payload + N runs when find() first asks for it, so everything downstream is unchanged.
     explicit TwoBitFile(const std::string &path);
     ~TwoBitFile();
     TwoBitFile(const TwoBitFile &) = delete;
     TwoBitFile &operator=(const TwoBitFile &) = delete;
-    int find(const std::string &name) const;                 // -1 if absent
+    int find(const std::string &name) const;                 // -1 if absent (nib directory: loads <name>.nib on demand)
     const std::vector<TwoBitSeq> &seqs() const { return seqs_; }
     const std::string &path() const { return path_; }
 private:
@@ -63,8 +67,11 @@ private:
     uint8_t *image_ = nullptr;
     size_t imageSize_ = 0;
     bool mapped_ = false;
-    std::vector<TwoBitSeq> seqs_;
-    std::unordered_map<std::string, int> index_;
+    bool nibDir_ = false;
+    mutable std::vector<TwoBitSeq> seqs_;
+    mutable std::unordered_map<std::string, int> index_;
+    mutable std::vector<std::vector<uint8_t>> nibPayload_;   // converted nib sequences (owned)
+    int loadNib(const std::string &name) const;
 };
 
 // Upload the sequences `use` (indices into tb.seqs(), in that order) with gat_load_genome.

@@ -340,7 +340,9 @@ public:
             const int ti = tbT.find(c.head.tName), qi = tbQ.find(c.head.qName);
             if (ti < 0) errAbort("%s is not in %s", c.head.tName.c_str(), tbT.path().c_str());
             if (qi < 0) errAbort("%s is not in %s", c.head.qName.c_str(), tbQ.path().c_str());
-            if (mapT[ti] < 0) { mapT[ti] = (int)useT.size(); useT.push_back(ti); }
+            if ((size_t)ti >= mapT.size()) mapT.resize(ti + 1, -1);
+        if ((size_t)qi >= mapQ.size()) mapQ.resize(qi + 1, -1);
+        if (mapT[ti] < 0) { mapT[ti] = (int)useT.size(); useT.push_back(ti); }
             if (mapQ[qi] < 0) { mapQ[qi] = (int)useQ.size(); useQ.push_back(qi); }
             c.tSeq = (uint32_t)mapT[ti];
             c.qSeq = (uint32_t)mapQ[qi];
@@ -653,8 +655,6 @@ static int toolMain(int argc, char **argv)
     const GapCalc gapCalc = GapCalc::fromFile(gapFileName);
     if (access(tNibDir, F_OK) != 0) errAbort("ERROR: target 2bit file or nib directory %s does not exist\n", tNibDir);
     if (access(qNibDir, F_OK) != 0) errAbort("ERROR: query 2bit file or nib directory %s does not exist\n", qNibDir);
-    if (!TwoBitFile::isTwoBit(tNibDir) || !TwoBitFile::isTwoBit(qNibDir))
-        errAbort("this build reads the genomes from .2bit files; nib directories (%s, %s) are not supported yet", tNibDir, qNibDir);
 
     // 0. net the chains ourselves if no net was given (chainCleaner.c:1639-1670)
     std::string tmpNet;

@@ -362,8 +362,6 @@ static int toolMain(int argc, char **argv)
         gapCalc = GapCalc::fromFile(gapFileName);
         verbose(1, "-rescore is set: read target/query genome from %s and %s. scoreSchemeName %s. gap costs %s.\n", tNibDir, qNibDir,
                 scoreSchemeName ? scoreSchemeName : "default", gapFileName);
-        if (!TwoBitFile::isTwoBit(tNibDir) || !TwoBitFile::isTwoBit(qNibDir))
-            errAbort("this build reads the genomes from .2bit files; nib directories (%s, %s) are not supported yet", tNibDir, qNibDir);
     }
 
     const char *chainFile = argv[1], *tSizes = argv[2], *qSizes = argv[3], *tNet = argv[4], *qNet = argv[5];
@@ -437,7 +435,9 @@ static int toolMain(int argc, char **argv)
             const int ti = tbT.find(h.tName), qi = tbQ.find(h.qName);
             if (ti < 0) errAbort("%s is not in %s", h.tName.c_str(), tNibDir);
             if (qi < 0) errAbort("%s is not in %s", h.qName.c_str(), qNibDir);
-            if (mapT[ti] < 0) { mapT[ti] = (int)useT.size(); useT.push_back(ti); }
+            if ((size_t)ti >= mapT.size()) mapT.resize(ti + 1, -1);
+        if ((size_t)qi >= mapQ.size()) mapQ.resize(qi + 1, -1);
+        if (mapT[ti] < 0) { mapT[ti] = (int)useT.size(); useT.push_back(ti); }
             if (mapQ[qi] < 0) { mapQ[qi] = (int)useQ.size(); useQ.push_back(qi); }
             chainT[c] = (uint32_t)mapT[ti];
             chainQ[c] = (uint32_t)mapQ[qi];

@@ -86,6 +86,8 @@ static int toolMain(int argc, char **argv)
         const int ti = tbT.find(h.tName), qi = tbQ.find(h.qName);
         if (ti < 0) errAbort("%s is not in %s", h.tName.c_str(), t2bit);
         if (qi < 0) errAbort("%s is not in %s", h.qName.c_str(), q2bit);
+        if ((size_t)ti >= mapT.size()) mapT.resize(ti + 1, -1);
+        if ((size_t)qi >= mapQ.size()) mapQ.resize(qi + 1, -1);
         if (mapT[ti] < 0) { mapT[ti] = (int)useT.size(); useT.push_back(ti); verbose(3, "\t\tLoaded %d bases of %s from %s\n", (int)tbT.seqs()[ti].size, h.tName.c_str(), t2bit); }
         if (mapQ[qi] < 0) { mapQ[qi] = (int)useQ.size(); useQ.push_back(qi); verbose(3, "\t\tLoaded %d bases of %s from %s\n", (int)tbQ.seqs()[qi].size, h.qName.c_str(), q2bit); }
         chainT[c] = (uint32_t)mapT[ti];

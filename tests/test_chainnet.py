@@ -83,3 +83,43 @@ def test_rescore_against_live_reference_binaries(golden, tmp_path, seed, gap, ma
     assert filecmp.cmp(str(tmp_path / "our.q.net"), str(tmp_path / "ref.q.net"), shallow=False)
     n_fill = sum(1 for l in open(tmp_path / "ref.t.net") if l.lstrip().startswith("fill"))
     assert n_fill > 1000
+
+
+def write_nib(path, genome, i):
+    """kent nib: sig, size, then two bases per byte, first base in the high nibble; T=0 C=1 A=2 G=3 N=4, +8 = masked."""
+    import struct
+    codes = genome.codes(i).astype(np.uint8)
+    for r in genome.n_runs[genome.n_runs["seq"] == i]:
+        codes[int(r["start"]):int(r["start"]) + int(r["len"])] = 4
+    for r in genome.mask_runs[genome.mask_runs["seq"] == i]:
+        codes[int(r["start"]):int(r["start"]) + int(r["len"])] |= 8
+    if len(codes) & 1:
+        codes = np.append(codes, np.uint8(0))
+    with open(path, "wb") as f:
+        f.write(struct.pack("<II", 0x6BE93D3A, int(genome.sizes[i])))
+        ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).tofile(f)
+
+
+@pytest.mark.gpu
+def test_rescore_from_nib_directories(golden, tmp_path):
+    """tNibDir / qNibDir may be directories of .nib files (chainNet.c:166-170): same nets as from .2bit."""
+    from genomealignmenttools_b200.twobit import PackedGenome
+    d = os.path.join(golden, "synth_small")
+    for side in ("t", "q"):
+        g = PackedGenome.read_2bit(os.path.join(d, side + ".2bit"))
+        os.makedirs(tmp_path / (side + "nib"))
+        for i, name in enumerate(g.names):
+            write_nib(tmp_path / (side + "nib") / (name + ".nib"), g, i)
+    t, q = str(tmp_path / "t.net"), str(tmp_path / "q.net")
+    r = run(EXE, ["-rescore", "-linearGap=medium", "-minSpace=5", "-minScore=0", "-tNibDir=" + str(tmp_path / "tnib"),
+                  "-qNibDir=" + str(tmp_path / "qnib"), os.path.join(d, "sorted.chain"), os.path.join(d, "t.sizes"),
+                  os.path.join(d, "q.sizes"), t, q])
+    assert r.returncode == 0, r.stderr
+    assert filecmp.cmp(t, os.path.join(d, "expected.t.net"), shallow=False)
+    assert filecmp.cmp(q, os.path.join(d, "expected.q.net"), shallow=False)
+    if os.path.exists(os.path.join(REFBIN, "chainNet")):     # and the reference reads our nib files the same way
+        rt, rq = str(tmp_path / "rt.net"), str(tmp_path / "rq.net")
+        subprocess.check_call([os.path.join(REFBIN, "chainNet"), "-rescore", "-linearGap=medium", "-minSpace=5", "-minScore=0",
+                               "-tNibDir=" + str(tmp_path / "tnib"), "-qNibDir=" + str(tmp_path / "qnib"), os.path.join(d, "sorted.chain"),
+                               os.path.join(d, "t.sizes"), os.path.join(d, "q.sizes"), rt, rq], stderr=subprocess.DEVNULL)
+        assert filecmp.cmp(rt, t, shallow=False)
