@@ -37,7 +37,7 @@ def log(*a):
 
 
 # --------------------------------------------------------------------------- workload
-def build_workload(blocks_per_gpu, world=1, plant=True):
+def build_workload(blocks_per_gpu, world=1, plant=True, mean_log_len=3.6, max_len=30000):
     """The whole job for `world` GPUs: world x blocks_per_gpu job-blocks (weak scaling), generated in
     `world` seeded parts so that N=1 is exactly part 0.  Every rank builds the identical set."""
     from genomealignmenttools_b200 import synth
@@ -48,7 +48,7 @@ def build_workload(blocks_per_gpu, world=1, plant=True):
     q = synth.random_genome(qn, qs, 0x5EED0002, telomere_n=10000)
     job_parts, block_parts, total = [], [], 0
     for part in range(world):
-        jobs, n, blocks = synth.make_chains(ts, qs, blocks_per_gpu, seed=0x5EED0050 + part)
+        jobs, n, blocks = synth.make_chains(ts, qs, blocks_per_gpu, seed=0x5EED0050 + part, mean_log_len=mean_log_len, max_len=max_len)
         if plant:
             synth.plant_homology(t, q, jobs, n, blocks, 0.30, 0x5EED0060 + part)
         synth.sprinkle_n_runs(t, "t", jobs, blocks, 0.0005, 0x5EED0070 + part)
@@ -247,6 +247,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-mbp", type=float, default=160.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mean-log-len", type=float, default=3.6, help="block length ~ lognormal(mu, 1.1); 3.6 = the benchmark (mean 67 bp)")
+    ap.add_argument("--max-len", type=int, default=30000)
+    ap.add_argument("--split", type=int, default=0, help="cut blocks longer than this into JOINED records (0 = as generated)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -291,7 +294,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    w, _ = shard_workload(build_workload(args.blocks, world), rank, world)
+    w, _ = shard_workload(build_workload(args.blocks, world, mean_log_len=args.mean_log_len, max_len=args.max_len), rank, world)
+    if args.split:
+        from genomealignmenttools_b200.records import split_long_blocks
+        bp = w.aligned_bp
+        w.alg_blocks = w.total
+        w.jobs, w.total, w.blocks = split_long_blocks(w.jobs, w.total, w.blocks, args.split)
+        assert w.aligned_bp == bp
     # our kernels launch on this torch stream, so torch's CUDA events bracket them
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)

@@ -461,11 +461,12 @@ static int checkDeviceError(gat_ctx *ctx)
     CU(cudaStreamSynchronize(ctx->stream));
     if (err) {
         cudaMemsetAsync(ctx->err, 0, sizeof(int), ctx->stream);
-        return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s%s",
+        return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s%s%s",
                     (err & ERR_SEQ) ? " sequence index out of range;" : "",
                     (err & ERR_BLOCKIDX) ? " block index out of range;" : "",
                     (err & ERR_COORD) ? " block coordinates outside their sequence;" : "",
-                    (err & ERR_TOOLONG) ? " a record of 2^20 bases or more (split it with GAT_BLOCK_JOINED);" : "");
+                    (err & ERR_TOOLONG) ? " a record of 2^20 bases or more (split it with GAT_BLOCK_JOINED);" : "",
+                    (err & ERR_CSR) ? " blockPtr is not a non-decreasing CSR row pointer starting at 0;" : "");
     }
     return GAT_OK;
 }

@@ -34,6 +34,7 @@ constexpr int P3_THREADS = CHUNK / RUN;
 constexpr int GROUP_BASES = 128;       // sequences start on a 32-byte sector boundary
 constexpr int PAD_FRONT_GROUPS = 1;    // '-' strand windows may start up to 31 bases early
 constexpr int PAD_BACK_GROUPS = 2;     // funnel shifts read one word past the last
+constexpr int LONG_ROUND_BASES = 1024;  // one warp-wide round of the long-block path (32 lanes x 32 bases)
 constexpr int NWIN_SHIFT = 8;          // N summary: one bit per 256 bases
 
 constexpr int ERR_SEQ = 1, ERR_BLOCKIDX = 2, ERR_COORD = 4;
@@ -284,7 +285,7 @@ __global__ void chunkIndexKernel(const gat_job *__restrict__ jobs, unsigned long
 // ------------------------------------------------------------------ the scoring kernel
 // n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | minus<<10 | mayN<<11; excl: items of the warp before this block
 struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
-constexpr int ERR_TOOLONG = 8;
+constexpr int ERR_TOOLONG = 8, ERR_CSR = 16;
 
 #ifndef GAT_MIN_CTAS
 #define GAT_MIN_CTAS 5
@@ -500,7 +501,11 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         const int v = warp * (32 * BPT) + sub * 32 + lane;
         const int pv = padIdx(v);
         const unsigned long long gv = vb0 + v;
-        const bool valid = gv < total;
+        bool valid = gv < total;
+        if (valid && sJob[pv] == 0) {       // blockPtr is not a non-decreasing CSR row pointer
+            atomicOr(P.err, ERR_CSR);
+            valid = false;
+        }
         uint32_t tW = 0, qW = 0, n = 0, misc = 0;
         unsigned char flag = 0;
         int ts = 0, qs = 0, len = 0;
@@ -579,6 +584,56 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     // ---- phase 2: the warp's 128 blocks as one list of 32-base items, dealt to lanes.
     // For the owner search lane l speaks for blocks 4l..4l+3 of the warp (consecutive), so their
     // exclusive item prefixes are a local prefix plus one warp scan.
+    const int warpV0 = warp * (32 * BPT);
+    // Long blocks first: whole rounds of 1024 bases of ONE block need no item bookkeeping at all --
+    // every lane takes one 32-base window per round, shifts and strand are warp-uniform, partial sums
+    // stay in a register until the block's bulk is done.  What is left (< 1024 bases) joins the item list.
+    {
+        __syncwarp();
+        const StageRec *mine = &sStage[warp][4 * lane];
+        unsigned longBits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) longBits |= ((mine[k].nMisc & 0xfffffu) >= 2u * LONG_ROUND_BASES ? 1u : 0u) << k;
+        for (int k = 0; k < 4; k++) {
+            unsigned m = __ballot_sync(FULL, (longBits >> k) & 1u);
+            while (m) {
+                const int o = 4 * (__ffs(m) - 1) + k;           // block index inside the warp (uniform)
+                m &= m - 1;
+                const StageRec r = sStage[warp][o];
+                const uint32_t n = r.nMisc & 0xfffffu, misc = r.nMisc >> 20;
+                const uint32_t rounds = n / LONG_ROUND_BASES;
+                const uint32_t tSh = misc & 31u, qSh = (misc >> 5) & 31u;
+                const bool minus = (misc >> 10) & 1u, mayN = (misc >> 11) & 1u;
+                long long acc = 0;
+                for (uint32_t rd = 0; rd < rounds; rd++) {
+                    const uint32_t w = rd * 32 + lane;
+                    uint32_t t1, t0, q1, q0;
+                    loadWindow(P.t.planes, r.tW + w, tSh, t1, t0);
+                    const uint32_t qn = minus ? r.qW - w : r.qW + w;
+                    loadWindow(P.q.planes, qn, qSh, q1, q0);
+                    if (minus) { q1 = ~__brev(q1); q0 = __brev(q0); }
+                    uint32_t vmask = 0xffffffffu;
+                    int nv = 32;
+                    if (mayN) {
+                        uint32_t nt = loadNWindow(P.t.nplane, r.tW + w, tSh);
+                        uint32_t nq = loadNWindow(P.q.nplane, qn, qSh);
+                        if (minus) nq = __brev(nq);
+                        vmask = ~(nt | nq);
+                        nv = __popc(vmask);
+                    }
+                    acc += scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
+                }
+                for (int off = 16; off; off >>= 1) acc += shfl64(acc, lane ^ off);
+                if (lane == 0) {
+                    sScore[padIdx(warpV0 + o)] += acc;
+                    const uint32_t done = rounds * LONG_ROUND_BASES, rem = n - done;
+                    sStage[warp][o] = StageRec{r.tW + rounds * 32, minus ? r.qW - rounds * 32 : r.qW + rounds * 32, rem | (misc << 20),
+                                               rem ? (rem + 31) >> 5 : 1u};
+                }
+                __syncwarp();
+            }
+        }
+    }
     uint32_t ex0, ex1, ex2, ex3, totalItems;
     {
         __syncwarp();
@@ -594,7 +649,6 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         st[0].excl = ex0; st[1].excl = ex1; st[2].excl = ex2; st[3].excl = ex3;
         __syncwarp();
     }
-    const int warpV0 = warp * (32 * BPT);
     {
         // Software pipeline: the loads of round r+1 are issued before round r is scored, so two
         // rounds of genome windows are in flight per warp.

@@ -636,14 +636,15 @@ void buildRecords(const ChainSet &cs, WorkList &wl)
     wl.blocks.clear();
     wl.blocks.reserve(cs.blocks.size());
     wl.chainFirstRecord.assign(cs.chains.size() + 1, 0);
-    const uint32_t maxPiece = GAT_MAX_BLOCK_BASES;
+    const uint32_t maxPiece = GAT_SPLIT_BASES;
     for (size_t c = 0; c < cs.chains.size(); c++) {
         wl.chainFirstRecord[c] = wl.blocks.size();
         const ChainHead &h = cs.chains[c];
         for (uint64_t i = 0; i < h.nBlocks; i++) {
             const gat_block &b = cs.blocks[h.firstBlock + i];
             if (b.size <= maxPiece) { wl.blocks.push_back(b); continue; }
-            // a gapless block too long for one device record: JOINED pieces score exactly like the block
+            // a long gapless block is cut into JOINED pieces (they score exactly like the block) so that its
+            // bases spread over many warps
             for (uint32_t off = 0; off < b.size; off += maxPiece) {
                 const uint32_t n = std::min(maxPiece, b.size - off);
                 wl.blocks.push_back(gat_block{b.tStart + (int)off, b.qStart + (int)off, n | (off ? GAT_BLOCK_JOINED : 0u)});
@@ -701,7 +702,7 @@ bool addSubChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, 
     uint64_t ra = wl.chainFirstRecord[c], re;
     if (wl.chainFirstRecord[c + 1] - wl.chainFirstRecord[c] == h.nBlocks) { ra += a; re = wl.chainFirstRecord[c] + e; }
     else {
-        auto pieces = [&](uint64_t i) { return (uint64_t)((b[i].size + GAT_MAX_BLOCK_BASES - 1) / GAT_MAX_BLOCK_BASES) + (b[i].size == 0); };
+        auto pieces = [&](uint64_t i) { return (uint64_t)((b[i].size + GAT_SPLIT_BASES - 1) / GAT_SPLIT_BASES) + (b[i].size == 0); };
         for (uint64_t i = 0; i < a; i++) ra += pieces(i);
         re = ra;
         for (uint64_t i = a; i < e; i++) re += pieces(i);

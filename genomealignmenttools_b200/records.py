@@ -49,3 +49,29 @@ def ali_bases(jobs, total_job_blocks, blocks):
     te = np.minimum(te, jobs["clipEnd"].astype(np.int64)[job_of])
     np.add.at(out, job_of, te - ts)
     return out
+
+
+SPLIT_BASES = 4096   # include/gat.h GAT_SPLIT_BASES
+
+
+def split_long_blocks(jobs, total_job_blocks, blocks, max_bases=SPLIT_BASES):
+    """Cut blocks longer than max_bases into JOINED records (what gathost::buildRecords does for the
+    tools).  Only for work-lists whose jobs tile the block array (firstBlock == blockPtr)."""
+    jobs = np.asarray(jobs); blocks = np.asarray(blocks)
+    assert np.array_equal(jobs["firstBlock"], jobs["blockPtr"]), "jobs must tile the block array"
+    size = (blocks["size"] & np.uint32(0x7FFFFFFF)).astype(np.int64)
+    pieces = np.maximum(1, (size + max_bases - 1) // max_bases)
+    if pieces.max() == 1:
+        return jobs, total_job_blocks, blocks
+    first = np.zeros(len(blocks) + 1, dtype=np.int64)
+    np.cumsum(pieces, out=first[1:])
+    src = np.repeat(np.arange(len(blocks)), pieces)
+    k = np.arange(first[-1]) - first[src]
+    out = np.zeros(first[-1], dtype=BLOCK_DTYPE)
+    out["tStart"] = blocks["tStart"][src] + k * max_bases
+    out["qStart"] = blocks["qStart"][src] + k * max_bases
+    out["size"] = np.minimum(max_bases, size[src] - k * max_bases).astype(np.uint32) | np.where(k > 0, np.uint32(BLOCK_JOINED), np.uint32(0))
+    new_jobs = jobs.copy()
+    new_jobs["firstBlock"] = first[jobs["firstBlock"].astype(np.int64)]
+    new_jobs["blockPtr"] = new_jobs["firstBlock"]
+    return new_jobs, int(first[-1]), out

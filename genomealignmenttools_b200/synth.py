@@ -167,11 +167,12 @@ class Workload:
 
     @property
     def aligned_bp(self):
-        return int(self.blocks["size"].astype(np.int64).sum())
+        return int((self.blocks["size"] & np.uint32(0x7FFFFFFF)).astype(np.int64).sum())
 
     def algorithmic_bytes(self):
         """0.5 B per aligned base pair + 12 B per block + 40 B per job."""
-        return 0.5 * self.aligned_bp + 12.0 * self.total + 40.0 * len(self.jobs)
+        # blocks cut into JOINED records for load balance still count once
+        return 0.5 * self.aligned_bp + 12.0 * getattr(self, "alg_blocks", self.total) + 40.0 * len(self.jobs)
 
 
 def make_workload(t_names, t_sizes, q_names, q_sizes, n_blocks, seed, telomere_n=10000, n_fraction=0.001,

@@ -43,8 +43,10 @@ extern "C" {
 #define GAT_BLOCK_JOINED 0x80000000u/* gat_block.size bit: this record continues the previous record's
                                      * gapless block (a long block split by the host for load
                                      * balance): no gap cost, no local-score clamp between them */
-#define GAT_MAX_BLOCK_BASES ((1u << 20) - 1) /* largest gat_block.size; longer gapless blocks are split
-                                             * into JOINED records by the host (gat_split_block below) */
+#define GAT_MAX_BLOCK_BASES ((1u << 20) - 1) /* largest gat_block.size the kernels accept */
+#define GAT_SPLIT_BASES 4096u                /* recommended record size: hosts cut longer gapless blocks into
+                                             * JOINED records of this many bases so that a few very long blocks
+                                             * spread over many warps (gathost::buildRecords does) */
 #define GAT_NO_CLIP_START INT32_MIN
 #define GAT_NO_CLIP_END INT32_MAX
 

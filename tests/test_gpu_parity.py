@@ -223,6 +223,13 @@ def test_empty_and_invalid_worklists():
         badj = w.jobs.copy(); badj["tSeq"][0] = 77
         with pytest.raises(GatError):
             sc.score(badj, w.total, w.blocks)
+        badp = w.jobs.copy(); badp["blockPtr"] = badp["blockPtr"][::-1].copy()
+        with pytest.raises(GatError) as e:
+            sc.score(badp, w.total, w.blocks)
+        assert e.value.code == -4
+        toolong = w.blocks.copy(); toolong["size"][0] = 1 << 20
+        with pytest.raises(GatError):
+            sc.score(w.jobs, w.total, toolong)
         g, l = sc.score(w.jobs, w.total, w.blocks)      # the context survives a rejected work-list
         g2, l2 = sc.score(w.jobs, w.total, w.blocks)
         assert np.array_equal(g, g2) and np.array_equal(l, l2)
