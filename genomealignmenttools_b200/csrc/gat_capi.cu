@@ -60,11 +60,13 @@ struct gat_ctx {
     gat_stats stats;
     gat_worklist *scratch = nullptr;   // device buffers of gat_score(), grown on demand and reused
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
+    uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
 };
 
 struct gat_worklist {
     uint64_t capJobs = 0, capBlocks = 0, capChunks = 0;   // allocated capacities (scratch reuse)
     gat_job *jobs = nullptr;
+    JobInfo *info = nullptr;            // jobs as the scoring kernel reads them (jobPrepKernel)
     gat_block *blocks = nullptr;
     uint64_t nJobs = 0, totalJobBlocks = 0, nBlocks = 0;
     uint32_t nChunks = 0;
@@ -76,9 +78,9 @@ struct gat_worklist {
 
 static void freeWorklistBuffers(gat_worklist *wl)
 {
-    cudaFree(wl->jobs); cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->chunkHead);
+    cudaFree(wl->jobs); cudaFree(wl->info); cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->chunkHead);
     cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal);
-    wl->jobs = nullptr; wl->blocks = nullptr; wl->chunkJob = nullptr; wl->chunkHead = wl->chunkTail = nullptr;
+    wl->jobs = nullptr; wl->info = nullptr; wl->blocks = nullptr; wl->chunkJob = nullptr; wl->chunkHead = wl->chunkTail = nullptr;
     wl->chunkTailJob = nullptr; wl->outGlobal = wl->outLocal = nullptr;
     wl->capJobs = wl->capBlocks = wl->capChunks = 0;
 }
@@ -277,9 +279,16 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
         if (s->longPos[i] <= s->longPos[i - 1]) return fail(GAT_EINVAL, "gat_set_scoring: longPos not increasing");
     for (int q = 0; q < 4; q++)
         for (int t = 0; t < 4; t++)
-            if (s->matrix[q][t] > (1 << 19) || s->matrix[q][t] < -(1 << 19))
-                return fail(GAT_EINVAL, "gat_set_scoring: |matrix| above 2^19 would overflow the 32-bit window sums");
+            if (s->matrix[q][t] > (1 << 18) || s->matrix[q][t] < -(1 << 18))
+                return fail(GAT_EINVAL, "gat_set_scoring: |matrix| above 2^18 would overflow the 32-bit sums of a GAT_SPLIT_BASES record");
     CU(cudaSetDevice(ctx->device));
+    {   // block sums are 32-bit on the device: records may hold at most (2^31-1)/max|M| bases
+        int maxAbs = 1;
+        for (int q = 0; q < 4; q++)
+            for (int t = 0; t < 4; t++) { const int a = s->matrix[q][t] < 0 ? -s->matrix[q][t] : s->matrix[q][t]; if (a > maxAbs) maxAbs = a; }
+        const uint32_t lim = (uint32_t)(0x7fffffff / maxAbs);
+        ctx->maxBlockBases = lim < GAT_MAX_BLOCK_BASES ? lim : GAT_MAX_BLOCK_BASES;
+    }
     ctx->sym = symmetricCoefs(s->matrix, ctx->coef);
     if (!ctx->sym) moebiusCoefs(s->matrix, ctx->coef);
     const int S = s->smallSize, L = s->longCount;
@@ -343,6 +352,7 @@ static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_
         const uint64_t cc = nChunks > wl->capChunks ? nChunks + nChunks / 8 : wl->capChunks;
         freeWorklistBuffers(wl);
         CU(cudaMalloc(&wl->jobs, (cj + 1) * sizeof(gat_job)));
+        CU(cudaMalloc(&wl->info, (cj + 1) * sizeof(JobInfo)));
         CU(cudaMalloc(&wl->blocks, (cb + 1) * sizeof(gat_block)));
         CU(cudaMalloc(&wl->chunkJob, (cc + 1) * sizeof(uint32_t)));
         CU(cudaMalloc(&wl->chunkHead, (cc + 1) * sizeof(Tup)));
@@ -411,10 +421,10 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
         return GAT_OK;
     }
     ScoreParams P;
-    P.jobs = wl->jobs; P.blocks = wl->blocks;
+    P.info = wl->info; P.blocks = wl->blocks;
     P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
     P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks;
-    P.prefetchChunks = ctx->residentCtas;
+    P.maxBlockBases = ctx->maxBlockBases;
     P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
     memcpy(P.coef, ctx->coef, sizeof P.coef);
     P.gap = ctx->gap;
@@ -426,8 +436,11 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     const bool prof = ctx->profiling;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
     {
-        unsigned grid = (unsigned)(((unsigned long long)wl->nChunks * 32 + 255) / 256);
-        chunkIndexKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->chunkJob, wl->nChunks);
+        const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
+        unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
+        jobPrepKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
+                                            (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
+                                            wl->outGlobal, wl->outLocal, ctx->err);
     }
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
     if (ctx->sym) scoreChunksKernel<true><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
@@ -435,8 +448,8 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     {
         unsigned grid = (unsigned)(((unsigned long long)wl->nChunks * 32 + 255) / 256);
-        fixupKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
-                                          wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal);
+        fixupKernel<<<grid, 256, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
+                                          wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
     }
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaGetLastError());
@@ -465,7 +478,7 @@ static int checkDeviceError(gat_ctx *ctx)
                     (err & ERR_SEQ) ? " sequence index out of range;" : "",
                     (err & ERR_BLOCKIDX) ? " block index out of range;" : "",
                     (err & ERR_COORD) ? " block coordinates outside their sequence;" : "",
-                    (err & ERR_TOOLONG) ? " a record of 2^20 bases or more (split it with GAT_BLOCK_JOINED);" : "",
+                    (err & ERR_TOOLONG) ? " a record longer than gat_max_record_bases() (split it with GAT_BLOCK_JOINED);" : "",
                     (err & ERR_CSR) ? " blockPtr is not a non-decreasing CSR row pointer starting at 0;" : "");
     }
     return GAT_OK;
@@ -512,6 +525,8 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
     }
     return rc;
 }
+
+extern "C" uint32_t gat_max_record_bases(const gat_ctx *ctx) { return ctx ? ctx->maxBlockBases : 0; }
 
 extern "C" int gat_synchronize(gat_ctx *ctx)
 {

@@ -29,21 +29,14 @@ constexpr int WARPS = TPB / 32;
 constexpr int BPT = 4;                 // job-blocks per thread = 32-block tiles per warp
 constexpr int CHUNK = TPB * BPT;       // job-blocks per CTA
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int RUN = 16;                // job-blocks per thread in the job reduction (phase 3)
-constexpr int P3_THREADS = CHUNK / RUN;
 constexpr int GROUP_BASES = 128;       // sequences start on a 32-byte sector boundary
-constexpr int PAD_FRONT_GROUPS = 1;    // '-' strand windows may start up to 31 bases early
-constexpr int PAD_BACK_GROUPS = 2;     // funnel shifts read one word past the last
-constexpr int LONG_ROUND_BASES = 1024;  // one warp-wide round of the long-block path (32 lanes x 32 bases)
+// Idle lanes of the last item round read up to 31 words beyond (or, on '-', before) the last block of a warp,
+// and funnel shifts read one word past a window: 36 words of slack at both ends of the genome buffers.
+constexpr int PAD_FRONT_GROUPS = 9;
+constexpr int PAD_BACK_GROUPS = 10;
 constexpr int NWIN_SHIFT = 8;          // N summary: one bit per 256 bases
 
-constexpr int ERR_SEQ = 1, ERR_BLOCKIDX = 2, ERR_COORD = 4;
-
-// shared-memory index of job-block v: one pad word per RUN so that phase 3 (thread t walks
-// v = RUN*t .. RUN*t+RUN-1) is bank-conflict free
-__device__ __forceinline__ int padIdx(int v) { return v + (v >> 4); }
-constexpr int PADDED = CHUNK + CHUNK / RUN + 2;
-static_assert(RUN == 16, "padIdx assumes RUN == 16");
+constexpr int ERR_SEQ = 1, ERR_BLOCKIDX = 2, ERR_COORD = 4, ERR_TOOLONG = 8, ERR_CSR = 16;
 
 struct GenomeView {
     const uint2 *planes;      // word n = {high bits, low bits} of bases [32n, 32n+32)
@@ -84,11 +77,11 @@ __device__ __forceinline__ Tup tupShfl(const Tup &t, int src)
 }
 
 // The same tuple in 32 bits, used by a warp whose 128 blocks are provably small enough
-// (sum of |block score| + gap cost below 2^28): a third of the instructions of the 64-bit form.
+// (sum of |block score| + gap cost below 2^27): a third of the instructions of the 64-bit form.
 template <typename T> struct TupT { T d, c, e, f; };
 template <typename T> __device__ __forceinline__ T negInf();
 template <> __device__ __forceinline__ long long negInf<long long>() { return NEG; }
-template <> __device__ __forceinline__ int negInf<int>() { return -(1 << 30); }
+template <> __device__ __forceinline__ int negInf<int>() { return -(1 << 29); }   // two of them still add without overflow
 template <typename T> __device__ __forceinline__ T maxT(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ TupT<T> tIdentity() { return TupT<T>{0, negInf<T>(), negInf<T>(), negInf<T>()}; }
 template <typename T> __device__ __forceinline__ TupT<T> tCombine(const TupT<T> &x, const TupT<T> &y)
@@ -106,9 +99,9 @@ template <typename T> __device__ __forceinline__ TupT<T> tShfl(const TupT<T> &t,
 {
     return TupT<T>{shflT(t.d, src), shflT(t.c, src), shflT(t.e, src), shflT(t.f, src)};
 }
-// to the 64-bit tuple that crosses warps / CTAs; anything at or below -2^29 is "minus infinity"
+// to the 64-bit tuple that crosses warps / CTAs; anything below -2^28 is "minus infinity"
 __device__ __forceinline__ long long widen(long long v) { return v; }
-__device__ __forceinline__ long long widen(int v) { return v < -(1 << 29) ? NEG : (long long)v; }
+__device__ __forceinline__ long long widen(int v) { return v < -(1 << 28) ? NEG : (long long)v; }
 template <typename T> __device__ __forceinline__ Tup tWiden(const TupT<T> &t) { return Tup{(long long)t.d, widen(t.c), widen(t.e), widen(t.f)}; }
 
 struct GapView {           // tables of struct gapCalc (gapCalc.c:12-37) as the device sees them
@@ -117,13 +110,22 @@ struct GapView {           // tables of struct gapCalc (gapCalc.c:12-37) as the 
     double lastVal[3], lastSlope[3];   // q, t, both
 };
 
+// A job as the scoring kernel reads it (written by jobPrepKernel): one 32-byte sector.
+struct __align__(16) JobInfo {
+    uint32_t tBaseW, qBaseW;    // index of the 32-base word that holds base 0 of the target / query sequence
+    uint32_t tSize, qSizeStrand;// sequence sizes; bit 31 of the latter = query on the '-' strand
+    int32_t clipStart, clipEnd;
+    uint32_t delta;             // firstBlock - blockPtr (mod 2^32): record index = job-block index + delta
+    uint32_t blockPtr;
+};
+
 struct ScoreParams {
-    const gat_job *jobs;
+    const JobInfo *info;        // [nJobs + 1], the last one closes the CSR
     const gat_block *blocks;
     unsigned long long nJobs, totalJobBlocks, nBlocks;
     const uint32_t *chunkJob;   // job containing the first job-block of each chunk
     uint32_t nChunks;
-    uint32_t prefetchChunks;    // how many chunks ahead a CTA prefetches work-list records (= resident CTAs)
+    uint32_t maxBlockBases;     // records longer than this are rejected (32-bit block sums)
     GenomeView t, q;
     int coef[16];               // SYM: 6 coefficients, general: 16 Moebius coefficients
     GapView gap;
@@ -204,6 +206,20 @@ __device__ __forceinline__ uint32_t shl1(uint32_t r)
     return out;
 }
 
+// 0xffffffff >> r for r < 32, else 0
+__device__ __forceinline__ uint32_t shrOnes(uint32_t r)
+{
+    uint32_t out;
+    asm("shr.b32 %0, 0xffffffff, %1;" : "=r"(out) : "r"(r));
+    return out;
+}
+// one step of an inclusive warp scan: x += (x of lane - off) where that lane exists
+__device__ __forceinline__ int scanStep(int x, int off)
+{
+    asm volatile("{ .reg .pred p; .reg .s32 y; shfl.sync.up.b32 y|p, %0, %1, 0, 0xffffffff; @p add.s32 %0, %0, y; }" : "+r"(x) : "r"(off));
+    return x;
+}
+
 // 32 bases starting `sh` bits into word n
 __device__ __forceinline__ void loadWindow(const uint2 *__restrict__ planes, uint32_t n, uint32_t sh,
                                            uint32_t &hi, uint32_t &lo)
@@ -217,11 +233,10 @@ __device__ __forceinline__ uint32_t loadNWindow(const uint32_t *__restrict__ np,
     return __funnelshift_r(__ldg(np + n), __ldg(np + n + 1), sh);
 }
 
-// does [g0, g0+len) touch a 256-base window that contains N?
-__device__ __forceinline__ bool mayTouchN(const uint32_t *__restrict__ nwin, long long g0, int len)
+// do the 32-base words wFirst..wLast touch a 256-base window (8 words) that contains N?
+__device__ __forceinline__ bool wordsTouchN(const uint32_t *__restrict__ nwin, uint32_t wFirst, uint32_t wLast)
 {
-    const uint32_t w0 = (uint32_t)((unsigned long long)g0 >> NWIN_SHIFT);          // genomes are < 2^36 bases
-    const uint32_t w1 = (uint32_t)((unsigned long long)(g0 + len - 1) >> NWIN_SHIFT);
+    const uint32_t w0 = wFirst >> 3, w1 = wLast >> 3;
     const uint32_t word0 = w0 >> 5, word1 = w1 >> 5;
     const uint32_t loMask = 0xffffffffu << (w0 & 31), hiMask = 0xffffffffu >> (31 - (w1 & 31));
     if (word0 == word1) return (__ldg(nwin + word0) & loMask & hiMask) != 0;     // blocks under 8 kb
@@ -258,58 +273,6 @@ __device__ __forceinline__ int scoreWindow(const int *coef, uint32_t t1, uint32_
     }
 }
 
-// ------------------------------------------------------------------ chunk index
-// chunkJob[c] = the job that owns job-block c*CHUNK = (first j with blockPtr[j] > v) - 1.
-// One warp per chunk, 32-ary search over the strided blockPtr column.
-__global__ void chunkIndexKernel(const gat_job *__restrict__ jobs, unsigned long long nJobs,
-                                 uint32_t *__restrict__ chunkJob, uint32_t nChunks)
-{
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nChunks) return;
-    unsigned long long target = (unsigned long long)warp * CHUNK;
-    unsigned long long lo = 0, hi = nJobs;   // invariant: blockPtr[lo] <= target, answer in [lo, hi)
-    while (hi - lo > 1) {
-        unsigned long long span = hi - lo, step = (span + 31) / 32;
-        unsigned long long idx = lo + lane * step;
-        bool le = idx < hi && (unsigned long long)__ldg(&jobs[idx].blockPtr) <= target;
-        unsigned m = __ballot_sync(FULL, le);
-        int k = __popc(m);                  // lanes 0..k-1 are <= target (blockPtr is monotone)
-        unsigned long long nlo = lo + (unsigned long long)(k - 1) * step;
-        unsigned long long nhi = nlo + step;
-        lo = nlo;
-        hi = nhi < hi ? nhi : hi;
-    }
-    if (lane == 0) chunkJob[warp] = (uint32_t)lo;
-}
-
-// ------------------------------------------------------------------ the scoring kernel
-// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | minus<<10 | mayN<<11; excl: items of the warp before this block
-struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
-constexpr int ERR_TOOLONG = 8, ERR_CSR = 16;
-
-#ifndef GAT_MIN_CTAS
-#define GAT_MIN_CTAS 5
-#endif
-#ifndef GAT_P1_UNROLL
-#define GAT_P1_UNROLL 2
-#endif
-#ifndef GAT_PREFETCH
-#define GAT_PREFETCH 1      // bit 0: genome windows from phase 1, bit 1: work-list records of a later chunk
-#endif
-constexpr int P1_UNROLL = GAT_P1_UNROLL;   // sub-tiles of phase 1 in flight per warp
-
-// chainFastSubsetOnT clip (chain.c:513-522) of one record for one job
-__device__ __forceinline__ void clipBlock(const gat_block &b, const gat_job &job, int &ts, int &qs, int &len, bool &joined)
-{
-    joined = (b.size & GAT_BLOCK_JOINED) != 0;
-    const int size = (int)(b.size & 0x7fffffffu);
-    ts = b.tStart; qs = b.qStart;
-    int te = ts + size;
-    if (ts < job.clipStart) { qs += job.clipStart - ts; ts = job.clipStart; }
-    if (te > job.clipEnd) te = job.clipEnd;
-    len = te - ts;
-}
-
 __device__ __forceinline__ gat_job loadJob(const gat_job *__restrict__ jobs, uint32_t j)
 {
     const uint2 *p = reinterpret_cast<const uint2 *>(jobs + j);     // 24-byte records, 8-byte aligned
@@ -326,50 +289,136 @@ __device__ __forceinline__ gat_block loadBlock(const gat_block *__restrict__ blo
     return r;
 }
 
-// Phase 3 of scoreChunksKernel for one warp (see there), in 32- or 64-bit tuples.
-template <typename T>
-__device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const long long *sScore, const int *sGap,
-                                              const unsigned char *sFlag, const uint32_t *sJob, int warpV0,
-                                              unsigned long long vb0, unsigned long long chunkEnd, int warp, int lane,
-                                              Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead, int *sWarpPendJob,
-                                              int *sLastIsEnd, uint32_t *sLastJob)
+// ------------------------------------------------------------------ job preparation
+// One thread per job: gat_job -> JobInfo (sequence bases and sizes resolved once per job instead of once
+// per block), zero scores for empty jobs (kent: NULL sub-chain), CSR validation, and chunkJob[c] = the job
+// that owns job-block c*CHUNK, written by the job itself for every chunk boundary it covers.
+__global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long long nJobs, unsigned long long total,
+                              const int64_t *__restrict__ tSeqBase, const uint32_t *__restrict__ tSeqSize, uint32_t tNSeq,
+                              const int64_t *__restrict__ qSeqBase, const uint32_t *__restrict__ qSeqSize, uint32_t qNSeq,
+                              JobInfo *__restrict__ info, uint32_t *__restrict__ chunkJob, uint32_t nChunks,
+                              long long *__restrict__ outGlobal, long long *__restrict__ outLocal, int *__restrict__ err)
 {
-    const T NEGT = negInf<T>();
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nJobs) return;
+    JobInfo o;
+    o.tBaseW = o.qBaseW = o.tSize = o.qSizeStrand = 0; o.clipStart = o.clipEnd = 0; o.delta = 0;
+    o.blockPtr = (uint32_t)total;                       // sentinel record nJobs closes the CSR
+    if (j < nJobs) {
+        const gat_job job = loadJob(jobs, (uint32_t)j);
+        const unsigned long long bp = job.blockPtr;
+        const unsigned long long np = (j + 1 < nJobs) ? (unsigned long long)__ldg(&jobs[j + 1].blockPtr) : total;
+        int e = 0;
+        if (np < bp || np > total || (j == 0 && bp != 0)) e |= ERR_CSR;
+        const uint32_t qSeq = job.qSeq & 0x7fffffffu;
+        o.blockPtr = job.blockPtr;
+        o.delta = job.firstBlock - job.blockPtr;
+        o.clipStart = job.clipStart; o.clipEnd = job.clipEnd;
+        if (job.tSeq >= tNSeq || qSeq >= qNSeq) {
+            if (np > bp) e |= ERR_SEQ;                  // sizes stay 0: every block of the job fails its range check
+        } else {
+            o.tBaseW = (uint32_t)(__ldg(tSeqBase + job.tSeq) >> 5);
+            o.qBaseW = (uint32_t)(__ldg(qSeqBase + qSeq) >> 5);
+            o.tSize = __ldg(tSeqSize + job.tSeq);
+            o.qSizeStrand = __ldg(qSeqSize + qSeq) | (job.qSeq & 0x80000000u);
+        }
+        if (e) atomicOr(err, e);
+        if (np <= bp) { outGlobal[j] = 0; outLocal[j] = 0; }
+        else if (!(e & ERR_CSR))
+            for (unsigned long long c = (bp + CHUNK - 1) / CHUNK; c * CHUNK < np && c < nChunks; c++) chunkJob[c] = (uint32_t)j;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(info + j);
+    dst[0] = make_uint4(o.tBaseW, o.qBaseW, o.tSize, o.qSizeStrand);
+    dst[1] = make_uint4((uint32_t)o.clipStart, (uint32_t)o.clipEnd, o.delta, o.blockPtr);
+}
+
+// ------------------------------------------------------------------ the scoring kernel
+// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | minus<<10 | mayN<<11; excl: items of the warp before this block
+struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
+
+#ifndef GAT_MIN_CTAS
+#define GAT_MIN_CTAS 5
+#endif
+#ifndef GAT_P1_UNROLL
+#define GAT_P1_UNROLL 2
+#endif
+#ifndef GAT_PREFETCH
+#define GAT_PREFETCH 1      // bit 0: first genome sectors of each block, from phase 1
+#endif
+constexpr int P1_UNROLL = GAT_P1_UNROLL;   // sub-tiles of phase 1 in flight per warp
+constexpr int TILE = 32 * BPT;             // job-blocks per warp
+constexpr int PASS_ITEMS = 1024;           // items covered by one register-resident head bitmap (32 rounds)
+
+__device__ __forceinline__ JobInfo loadInfo(const JobInfo *__restrict__ info, uint32_t j)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(info + j);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    JobInfo r;
+    r.tBaseW = a.x; r.qBaseW = a.y; r.tSize = a.z; r.qSizeStrand = a.w;
+    r.clipStart = (int)b.x; r.clipEnd = (int)b.y; r.delta = b.z; r.blockPtr = b.w;
+    return r;
+}
+
+// chainFastSubsetOnT clip (chain.c:513-522) of one record for one job; te/qe = clipped ends
+__device__ __forceinline__ void clipBlock(const gat_block &b, int clipStart, int clipEnd, int &ts, int &qs, int &len, bool &joined)
+{
+    joined = (b.size & GAT_BLOCK_JOINED) != 0;
+    const int size = (int)(b.size & 0x7fffffffu);
+    ts = b.tStart; qs = b.qStart;
+    int te = ts + size;
+    if (ts < clipStart) { qs += clipStart - ts; ts = clipStart; }
+    if (te > clipEnd) te = clipEnd;
+    len = te - ts;
+}
+
+template <typename T> __device__ __forceinline__ long long finalLocal(const TupT<T> &t)
+{   // a job's running score ends at max(c, d) (entered with 0) and its last peak test is still due
+    return max64(0, max64(max64(widen(t.c), (long long)t.d), max64(widen(t.e), widen(t.f))));
+}
+__device__ __forceinline__ long long finalLocal(const Tup &t) { return max64(0, max64(max64(t.c, t.d), max64(t.e, t.f))); }
+
+// Phase 3 of scoreChunksKernel for one warp (see there), in 32- or 64-bit tuples.  Lane l holds job-blocks
+// 4l..4l+3 of the warp: scores a[], gap costs g[] (the gap BEFORE the block), flags fl4 (one byte each).
+template <typename T>
+__device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
+                                              uint32_t myWr, uint32_t myHw, const uint32_t *sJobSlot, int warpV0, int vEnd,
+                                              int warp, int lane, Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead,
+                                              int *sWarpPendJob, int *sLastIsEnd, uint32_t *sLastJob)
+{
     TupT<T> cur = tIdentity<T>();     // open segment at the end of my run
     bool runHasHead = false;
     bool pend = false;                // an END reached before any HEAD of my run: needs the carry
     TupT<T> pendTup = tIdentity<T>();
     uint32_t pendJob = 0;
-    {
-        const int o0 = 4 * lane;
-        int p = padIdx(warpV0 + o0);
 #pragma unroll
-        for (int k = 0; k < 4; k++, p++) {
-            const unsigned char fl = sFlag[p];
-            if (fl & 8) {
-                const T a = (T)sScore[p];
-                const bool isEnd = fl & 2, joinedNext = fl & 4;
-                T dY = a, cY = NEGT;
-                if (!isEnd && !joinedNext) { dY = a - (T)sGap[p]; cY = 0; }
-                if (fl & 1) { cur = tIdentity<T>(); runHasHead = true; }
-                // cur = cur (+) element, specialised for a single block (its f is -inf)
+    for (int k = 0; k < BPT; k++) {
+        const uint32_t fl = (fl4 >> (8 * k)) & 0xffu;
+        if (fl & 8) {
+            const T av = (T)a[k];
+            if (fl & 1) { cur = tIdentity<T>(); runHasHead = true; }
+            if (fl & 5) {             // first block of the job, or the continuation of a split block: plain add
+                cur.d += av; cur.c += av;
+            } else {                  // peak test of the previous block, gap, clamp at 0, add (scoreChain.c:181-195)
+                const T dY = av - (T)g[k];
                 TupT<T> r;
+                r.e = maxT<T>(cur.e, cur.d);
+                r.f = maxT<T>(cur.f, cur.c);
+                r.c = maxT<T>(av, cur.c + dY);
                 r.d = cur.d + dY;
-                r.c = maxT<T>(cY, cur.c + dY);
-                r.e = joinedNext ? cur.e : maxT<T>(cur.e, cur.d + a);
-                r.f = joinedNext ? cur.f : maxT<T>(cur.f, cur.c + a);
                 cur = r;
-                if (isEnd) {
-                    const uint32_t job = sJob[p] - 1;
-                    if (runHasHead) {   // job lies inside my run: done
-                        P.outGlobal[job] = (long long)cur.d;
-                        P.outLocal[job] = max64(0, max64(widen(cur.e), widen(cur.f)));
-                    } else { pend = true; pendTup = cur; pendJob = job; }
-                }
-                if (vb0 + (unsigned long long)(warpV0 + o0 + k) + 1 == chunkEnd) {
-                    *sLastIsEnd = isEnd;                // the chunk's last valid job-block
-                    *sLastJob = sJob[p] - 1;
-                }
+            }
+            const int v = warpV0 + BPT * lane + k;
+            if (fl & 2) {
+                const uint32_t rank = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31)))) - 1;
+                const uint32_t job = sJobSlot[rank];
+                if (runHasHead) {   // job lies inside my run: done
+                    P.outGlobal[job] = (long long)cur.d;
+                    P.outLocal[job] = finalLocal(cur);
+                } else { pend = true; pendTup = cur; pendJob = job; }
+                if (v + 1 == vEnd) { *sLastIsEnd = 1; *sLastJob = job; }
+            } else if (v + 1 == vEnd) {          // the chunk's last valid job-block: its job runs on
+                const uint32_t rank = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31)))) - 1;
+                *sLastIsEnd = 0; *sLastJob = sJobSlot[rank];
             }
         }
     }
@@ -388,7 +437,7 @@ __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const long l
         const TupT<T> fin = tCombine<T>(carry, pendTup);
         if (carryHead) {            // the job started inside this warp
             P.outGlobal[pendJob] = (long long)fin.d;
-            P.outLocal[pendJob] = max64(0, max64(widen(fin.e), widen(fin.f)));
+            P.outLocal[pendJob] = finalLocal(fin);
         } else {                    // it started before this warp: at most one such lane per warp
             sWarpPend[warp] = tWiden<T>(fin); sWarpPendJob[warp] = (int)pendJob;
         }
@@ -404,43 +453,29 @@ template <bool SYM>
 __global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
 scoreChunksKernel(const __grid_constant__ ScoreParams P)
 {
-    // per job-block of the chunk, index padIdx(v)
-    __shared__ uint32_t sJob[PADDED];           // job index + 1
-    __shared__ long long sScore[PADDED];        // block score (accumulated by the item loop)
-    __shared__ int sGap[PADDED];                // cost of the gap that follows the block
-    __shared__ unsigned char sFlag[PADDED];     // 1 head of job, 2 end of job, 4 next record joined, 8 valid
-    // per warp: its 128 blocks expanded to items
-    __shared__ StageRec sStage[WARPS][32 * BPT];
-    __shared__ int sAcc[WARPS][32 * BPT];
-    __shared__ uint32_t sWarpMax[WARPS];
+    __shared__ uint32_t sHead[CHUNK / 32 + 1];  // bit v: a job starts at job-block v of the chunk (bit 0: always; bit vEnd: end of list)
+    __shared__ uint32_t sJobSlot[CHUNK + 1];    // job index of the r-th head
+    __shared__ __align__(16) int sGap[CHUNK];   // cost of the gap in front of the block
+    __shared__ __align__(16) int sScore[CHUNK]; // block score: first 32 bases from phase 1, the rest added after phase 2
+    __shared__ __align__(16) int sEnd[CHUNK];   // per list slot: running item-score sum of the warp at the slot's last item (mod 2^32)
+    __shared__ unsigned char sSlotV[CHUNK];     // per list slot: its block (index inside the warp's tile)
+    __shared__ __align__(4) unsigned char sFlag[CHUNK];   // 1 head of job, 2 end of job, 4 continues the previous record, 8 valid
+    __shared__ StageRec sStage[WARPS][TILE];    // per warp: its blocks expanded to items
+    __shared__ uint32_t sBits[WARPS][32];       // scratch for the item-head bitmap of a pass
     __shared__ Tup sWarpAgg[WARPS], sWarpPend[WARPS];
     __shared__ int sWarpHead[WARPS], sWarpPendJob[WARPS];
-    __shared__ int sArrived, sLastIsEnd;
+    __shared__ int sArrived, sLastIsEnd, sFirstIsHead;
     __shared__ uint32_t sLastJob;
     extern __shared__ unsigned char sDyn[];     // gap tables
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long vb0 = (unsigned long long)blockIdx.x * CHUNK;
-    const unsigned long long total = P.totalJobBlocks;
+    if (*reinterpret_cast<volatile const int *>(P.err)) return;     // jobPrepKernel rejected the work-list
+    const uint32_t vb0 = blockIdx.x * (uint32_t)CHUNK;               // totalJobBlocks < 2^32
+    const uint32_t total = (uint32_t)P.totalJobBlocks;
+    const int vEnd = (int)(total - vb0 < (uint32_t)CHUNK ? total - vb0 : (uint32_t)CHUNK);   // valid job-blocks of this chunk
     if (tid == 0) sArrived = 0;
+    for (int i = tid; i < CHUNK / 32 + 1; i += TPB) sHead[i] = 0;
 
-#if GAT_PREFETCH & 2
-    {   // the records of the chunk that will run when this one retires: stream them into L2 now
-        const unsigned long long ahead = vb0 + (unsigned long long)P.prefetchChunks * CHUNK;
-        if (ahead < total) {
-            const char *b0 = reinterpret_cast<const char *>(P.blocks + ahead);        // whole-chain work-lists: record index == job-block index
-            const unsigned long long bytes = ((total - ahead < (unsigned long long)CHUNK) ? total - ahead : (unsigned long long)CHUNK) * sizeof(gat_block);
-            for (unsigned long long off = (unsigned long long)tid * 32; off < bytes; off += TPB * 32) prefetchL2(b0 + off);
-            const uint32_t ca = blockIdx.x + P.prefetchChunks;
-            if (warp == 0 && ca + 1 < P.nChunks) {
-                const uint32_t ja = __ldg(P.chunkJob + ca), jb = __ldg(P.chunkJob + ca + 1);
-                const char *j0p = reinterpret_cast<const char *>(P.jobs + ja);
-                const unsigned long long jbytes = (unsigned long long)(jb - ja + 1) * sizeof(gat_job);
-                for (unsigned long long off = (unsigned long long)lane * 32; off < jbytes; off += 32 * 32) prefetchL2(j0p + off);
-            }
-        }
-    }
-#endif
     // ---- stage gap tables (gapCalc.c:12-37) in shared memory
     double *gLongVal = reinterpret_cast<double *>(sDyn);
     int *gLongPos = reinterpret_cast<int *>(gLongVal + 3 * P.gap.longCount);
@@ -451,264 +486,265 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     for (int i = tid; i < P.gap.longCount; i += TPB) gLongPos[i] = P.gapLongPos[i];
 #pragma unroll 1
     for (int i = tid; i < 3 * P.gap.smallSize; i += TPB) gSmall[i] = P.gapSmall[i];
-
-    // ---- phase 0: which job owns each job-block of this chunk
-#pragma unroll 1
-    for (int i = tid; i < PADDED; i += TPB) sJob[i] = 0;
     __syncthreads();
+
+    // ---- phase 0: where jobs start inside this chunk (bitmap), and which job the r-th start is
+    const uint32_t j0 = __ldg(P.chunkJob + blockIdx.x);
+    const uint32_t jEnd = (blockIdx.x + 1 < P.nChunks) ? __ldg(P.chunkJob + blockIdx.x + 1) : (uint32_t)(P.nJobs - 1);
+    if (tid == 0) {
+        atomicOr(&sHead[0], 1u);                                       // the chunk's first block opens slot 0
+        if (vb0 + (uint32_t)vEnd == total) atomicOr(&sHead[vEnd >> 5], 1u << (vEnd & 31));   // nothing follows the last block
+        sFirstIsHead = __ldg(&P.info[j0].blockPtr) == vb0;
+    }
+    for (uint32_t j = j0 + tid; j <= jEnd; j += TPB) {
+        const uint32_t bp = __ldg(&P.info[j].blockPtr), np = __ldg(&P.info[j + 1].blockPtr);
+        if (np > bp && bp > vb0 && bp - vb0 <= (uint32_t)CHUNK) atomicOr(&sHead[(bp - vb0) >> 5], 1u << ((bp - vb0) & 31));
+    }
+    __syncthreads();
+    uint32_t wrank;                                                    // lane i: heads in words 0..i-1
     {
-        const uint32_t j0 = P.chunkJob[blockIdx.x];
-        const uint32_t jEnd = (blockIdx.x + 1 < P.nChunks) ? P.chunkJob[blockIdx.x + 1] : (uint32_t)(P.nJobs - 1);
-        const uint32_t jStart = blockIdx.x == 0 ? 0u : j0;   // chunk 0 also sweeps leading empty jobs
-        for (uint32_t j = jStart + tid; j <= jEnd; j += TPB) {
-            unsigned long long bp = __ldg(&P.jobs[j].blockPtr);
-            unsigned long long np = (j + 1 < P.nJobs) ? (unsigned long long)__ldg(&P.jobs[j + 1].blockPtr) : total;
-            if (np > bp) {                                  // non-empty job
-                if (bp >= vb0 && bp < vb0 + CHUNK) sJob[padIdx((int)(bp - vb0))] = j + 1;
-                else if (bp < vb0 && j == j0) sJob[0] = j + 1;
-            } else {                                        // empty job (kent: NULL sub-chain): scores 0
-                P.outGlobal[j] = 0;
-                P.outLocal[j] = 0;
-            }
-        }
-    }
-    __syncthreads();
-    {   // inclusive max-scan: job indices grow with position, so max = nearest head at or before
-        const int i0 = padIdx(4 * tid);                     // 4 consecutive job-blocks never straddle a pad
-        uint32_t m0 = sJob[i0], m1 = max(m0, sJob[i0 + 1]), m2 = max(m1, sJob[i0 + 2]), m3 = max(m2, sJob[i0 + 3]);
-        uint32_t run = m3;
+        const uint32_t pc = __popc(sHead[lane]);
+        uint32_t inc = pc;
         for (int off = 1; off < 32; off <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, run, off);
-            if (lane >= off) run = max(run, o);
+            const uint32_t o = __shfl_up_sync(FULL, inc, off);
+            if (lane >= off) inc += o;
         }
-        if (lane == 31) sWarpMax[warp] = run;
-        uint32_t before = __shfl_up_sync(FULL, run, 1);
-        if (lane == 0) before = 0;
-        __syncthreads();
-        for (int w = 0; w < warp; w++) before = max(before, sWarpMax[w]);
-        sJob[i0] = max(m0, before);
-        sJob[i0 + 1] = max(m1, before);
-        sJob[i0 + 2] = max(m2, before);
-        sJob[i0 + 3] = max(m3, before);
+        wrank = inc - pc;
+    }
+    for (uint32_t base = j0; base <= jEnd; base += TPB) {              // warp-uniform trip count (shuffle inside)
+        const uint32_t j = base + tid;
+        bool act = j <= jEnd;
+        uint32_t pos = 0;
+        if (act) {
+            const uint32_t bp = __ldg(&P.info[j].blockPtr), np = __ldg(&P.info[j + 1].blockPtr);
+            act = np > bp && (bp > vb0 ? bp - vb0 < (uint32_t)CHUNK : j == j0);
+            pos = bp > vb0 ? bp - vb0 : 0u;
+        }
+        const uint32_t wsel = (pos >> 5) & 31u;
+        const uint32_t wr = __shfl_sync(FULL, wrank, wsel);
+        if (act) sJobSlot[wr + __popc(sHead[wsel] & ((1u << (pos & 31)) - 1u))] = j;
     }
     __syncthreads();
 
-    // ---- phase 1: this warp's 128 job-blocks, 32 at a time: load + clip the records, gap costs,
-    // item counts.  Block v = warp*128 + sub*32 + lane.
+    // ---- phase 1: this warp's TILE job-blocks, 32 at a time: load + clip the records, gap costs,
+    // item counts.  Block v = warp*TILE + sub*32 + lane.
     bool anyN = false;
+    int nSlots = 0;                     // blocks of this warp with more than 32 bases: they get a slot in the item list
+    int carryTe = 0, carryQe = 0;       // clipped ends of the previous sub-tile's last block
 #pragma unroll P1_UNROLL
     for (int sub = 0; sub < BPT; sub++) {
-        const int v = warp * (32 * BPT) + sub * 32 + lane;
-        const int pv = padIdx(v);
-        const unsigned long long gv = vb0 + v;
-        bool valid = gv < total;
-        if (valid && sJob[pv] == 0) {       // blockPtr is not a non-decreasing CSR row pointer
-            atomicOr(P.err, ERR_CSR);
-            valid = false;
-        }
+        const int wi = warp * BPT + sub;
+        const int v = wi * 32 + lane;
+        const uint32_t hw = sHead[wi], hwn = sHead[wi + 1];
+        const uint32_t wr = __shfl_sync(FULL, wrank, wi);
+        const bool valid = v < vEnd;
         uint32_t tW = 0, qW = 0, n = 0, misc = 0;
         unsigned char flag = 0;
         int ts = 0, qs = 0, len = 0;
         bool joined = false;
-        gat_job job;
-        job.tSeq = job.qSeq = job.firstBlock = job.blockPtr = 0; job.clipStart = job.clipEnd = 0;
+        JobInfo job;
+        job.tBaseW = job.qBaseW = job.tSize = job.qSizeStrand = job.delta = job.blockPtr = 0; job.clipStart = job.clipEnd = 0;
+        uint32_t bi = 0;
         if (valid) {
-            const uint32_t j = sJob[pv] - 1;
-            job = loadJob(P.jobs, j);
+            const uint32_t rank = wr + __popc(hw & (0xffffffffu >> (31 - lane))) - 1;
+            job = loadInfo(P.info, sJobSlot[rank]);
             flag = 8;
-            if (gv == job.blockPtr) flag |= 1;
-            // end of job <=> the next job-block belongs to another job (or there is none)
-            if (v + 1 < CHUNK) { if (gv + 1 >= total || sJob[padIdx(v + 1)] - 1 != j) flag |= 2; }
+            if (v == 0 ? sFirstIsHead != 0 : ((hw >> lane) & 1u) != 0) flag |= 1;
+            if (lane < 31 ? ((hw >> (lane + 1)) & 1u) != 0 : (hwn & 1u) != 0) flag |= 2;
+            bi = vb0 + (uint32_t)v + job.delta;
+            if ((unsigned long long)bi >= P.nBlocks) { atomicOr(P.err, ERR_BLOCKIDX); }
             else {
-                const unsigned long long np = (j + 1 < P.nJobs) ? (unsigned long long)__ldg(&P.jobs[j + 1].blockPtr) : total;
-                if (gv + 1 == np) flag |= 2;
-            }
-            const unsigned long long bi = (unsigned long long)job.firstBlock + (gv - job.blockPtr);
-            const uint32_t qSeq = job.qSeq & 0x7fffffffu;
-            const bool minus = (job.qSeq >> 31) != 0;
-            if (bi >= P.nBlocks) { atomicOr(P.err, ERR_BLOCKIDX); }
-            else if (job.tSeq >= P.t.nSeq || qSeq >= P.q.nSeq) { atomicOr(P.err, ERR_SEQ); }
-            else {
-                clipBlock(loadBlock(P.blocks, bi), job, ts, qs, len, joined);
+                clipBlock(loadBlock(P.blocks, bi), job.clipStart, job.clipEnd, ts, qs, len, joined);
                 const int nn = len > 0 ? len : 0;
-                const uint32_t tSize = __ldg(P.t.seqSize + job.tSeq), qSize = __ldg(P.q.seqSize + qSeq);
+                const uint32_t tSize = job.tSize, qSize = job.qSizeStrand & 0x7fffffffu;
+                const bool minus = (job.qSizeStrand >> 31) != 0;
                 if (nn > 0 && (ts < 0 || qs < 0 || (unsigned)ts + (unsigned)nn > tSize || (unsigned)qs + (unsigned)nn > qSize)) {
                     atomicOr(P.err, ERR_COORD);
-                } else if (nn >= (1 << 20)) {
+                } else if ((uint32_t)nn > P.maxBlockBases) {
                     atomicOr(P.err, ERR_TOOLONG);
                 } else if (nn > 0) {
                     n = (uint32_t)nn;
-                    const long long tG = __ldg(P.t.seqBase + job.tSeq) + ts;
                     // '+': first base of the block.  '-': one past the block's last base in forward
                     // coordinates; rc position p is forward position qSize-1-p (dnautil.c:466-470).
-                    const long long qBase = __ldg(P.q.seqBase + qSeq);
-                    const long long qG = minus ? qBase + ((long long)qSize - qs) : qBase + qs;
-                    const long long qLo = minus ? qG - nn : qG;
-                    const bool mayN = mayTouchN(P.t.nwin, tG, nn) || mayTouchN(P.q.nwin, qLo, nn);
-                    tW = (uint32_t)(tG >> 5);
-                    qW = minus ? (uint32_t)((qG - 32) >> 5) : (uint32_t)(qG >> 5);
-                    misc = (uint32_t)(tG & 31) | ((uint32_t)(qG & 31) << 5) | (minus ? 1u << 10 : 0u) | (mayN ? 1u << 11 : 0u);
+                    const uint32_t qAt = minus ? qSize - (uint32_t)qs : (uint32_t)qs;      // local coordinate
+                    const uint32_t qLo = minus ? qAt - n : qAt;
+                    const uint32_t tSh = (uint32_t)ts & 31u, qSh = qAt & 31u;
+                    tW = job.tBaseW + ((uint32_t)ts >> 5);
+                    qW = minus ? job.qBaseW + (uint32_t)(((int)qAt - 32) >> 5) : job.qBaseW + (qAt >> 5);
+                    const bool mayN = wordsTouchN(P.t.nwin, tW, tW + ((tSh + n - 1) >> 5)) ||
+                                      wordsTouchN(P.q.nwin, job.qBaseW + (qLo >> 5), job.qBaseW + ((qLo + n - 1) >> 5));
+                    misc = tSh | (qSh << 5) | (minus ? 1u << 10 : 0u) | (mayN ? 1u << 11 : 0u);
                     anyN |= mayN;
 #if GAT_PREFETCH & 1
-                    // phase 2 reads these windows a few microseconds from now: pull the first sectors into L2
-                    prefetchL2(P.t.planes + tW);
-                    prefetchL2(P.q.planes + (minus ? qW + 1 : qW));
+                    // phase 2 reads the rest of the block a few microseconds from now: pull its last sector into L2
+                    if (n > 32) {
+                        const uint32_t lastItem = (n - 1) >> 5;
+                        prefetchL2(P.t.planes + tW + lastItem);
+                        prefetchL2(P.q.planes + (minus ? qW - lastItem : qW + lastItem + 1));
+                    }
 #endif
                 }
             }
         }
-        // the block after mine (same job): lane+1 holds it; lane 31 fetches it itself
-        int nts = __shfl_down_sync(FULL, ts, 1), nqs = __shfl_down_sync(FULL, qs, 1);
-        bool njoined = __shfl_down_sync(FULL, (int)joined, 1);
-        if (lane == 31 && valid && !(flag & 2)) {
-            const unsigned long long bi = (unsigned long long)job.firstBlock + (gv + 1 - job.blockPtr);
-            nts = nqs = 0; njoined = false;
-            if (bi < P.nBlocks) {
-                int nlen;
-                clipBlock(loadBlock(P.blocks, bi), job, nts, nqs, nlen, njoined);
+        // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
+        // last block, or fetches it when this is the warp's first sub-tile
+        const int te = ts + len, qe = qs + len;
+        int pte = __shfl_up_sync(FULL, te, 1), pqe = __shfl_up_sync(FULL, qe, 1);
+        if (lane == 0) {
+            pte = carryTe; pqe = carryQe;
+            if (sub == 0 && valid && !(flag & 1) && bi > 0 && (unsigned long long)bi < P.nBlocks) {
+                int pts, pqs, plen; bool pj;
+                clipBlock(loadBlock(P.blocks, bi - 1), job.clipStart, job.clipEnd, pts, pqs, plen, pj);
+                pte = pts + plen; pqe = pqs + plen;
             }
         }
+        carryTe = __shfl_sync(FULL, te, 31); carryQe = __shfl_sync(FULL, qe, 31);
         int gap = 0;
-        if (valid && !(flag & 2)) {
-            if (njoined) flag |= 4;
-            else gap = gapCost(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, nqs - (qs + len), nts - (ts + len));
+        if (valid && !(flag & 1)) {
+            if (joined) flag |= 4;
+            else gap = gapCost(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, qs - pqe, ts - pte);
         }
-        sGap[pv] = gap;
-        sFlag[pv] = flag;
-        sScore[pv] = 0;
-        sStage[warp][sub * 32 + lane] = StageRec{tW, qW, n | (misc << 20), n ? (n + 31) >> 5 : 1u};   // excl = item count for now
-        sAcc[warp][sub * 32 + lane] = 0;
+        sGap[v] = gap;
+        sFlag[v] = flag;
+        // the block's first 32 bases are scored right here (lane = block, no item bookkeeping);
+        // only what is left joins the warp's item list
+        const bool minus = (misc >> 10) & 1u;
+        int s0 = 0;
+        if (n) {
+            const uint32_t tSh = misc, qSh = misc >> 5;          // funnel shifts use the low 5 bits
+            uint32_t t1, t0, q1, q0;
+            loadWindow(P.t.planes, tW, tSh, t1, t0);
+            loadWindow(P.q.planes, qW, qSh, q1, q0);
+            const uint32_t r1 = ~__brev(q1), r0 = __brev(q0);     // reverse, complement = flip bit1
+            q1 = minus ? r1 : q1; q0 = minus ? r0 : q0;
+            uint32_t vmask = shrOnes(n >= 32 ? 0u : 32u - n);
+            int nv = n >= 32 ? 32 : (int)n;
+            if ((misc >> 11) & 1u) {
+                uint32_t nt = loadNWindow(P.t.nplane, tW, tSh);
+                uint32_t nq = loadNWindow(P.q.nplane, qW, qSh);
+                if (minus) nq = __brev(nq);
+                vmask &= ~(nt | nq);            // N scores 0 against everything (axt.c:431-454)
+                nv = __popc(vmask);
+            }
+            s0 = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
+        }
+        sScore[v] = s0;
+        const bool listed = n > 32;
+        const uint32_t lb = __ballot_sync(FULL, listed);
+        if (listed) {
+            const int slot = nSlots + __popc(lb & ((1u << lane) - 1u));
+            sStage[warp][slot] = StageRec{tW + 1, minus ? qW - 1 : qW + 1, (n - 32) | (misc << 20), (n - 1) >> 5};   // excl = item count for now
+            sSlotV[warp * TILE + slot] = (unsigned char)(sub * 32 + lane);
+        }
+        nSlots += __popc(lb);
     }
     anyN = __any_sync(FULL, anyN);
 
-    // ---- phase 2: the warp's 128 blocks as one list of 32-base items, dealt to lanes.
-    // For the owner search lane l speaks for blocks 4l..4l+3 of the warp (consecutive), so their
-    // exclusive item prefixes are a local prefix plus one warp scan.
-    const int warpV0 = warp * (32 * BPT);
-    // Long blocks first: whole rounds of 1024 bases of ONE block need no item bookkeeping at all --
-    // every lane takes one 32-base window per round, shifts and strand are warp-uniform, partial sums
-    // stay in a register until the block's bulk is done.  What is left (< 1024 bases) joins the item list.
-    {
-        __syncwarp();
-        const StageRec *mine = &sStage[warp][4 * lane];
-        unsigned longBits = 0;
+    // ---- phase 2: what is left of the warp's blocks as one list of 32-base items, dealt to lanes round
+    // by round (adjacent lanes = adjacent items: coalesced).  Lane l speaks for list slots 4l..4l+3 when the
+    // item prefix is built.  Per pass of 1024 items the bit "this list position starts a block" lives in
+    // one register per lane (lane r: round r), so the owner of an item is one shuffle and two popcounts.
+    // Scores leave the loop as a running prefix sum stored at each slot's last item: no atomics.
+    const int warpV0 = warp * TILE;
+    if (nSlots) {
+        uint32_t totalItems;
+        StageRec *st = &sStage[warp][BPT * lane];
+        {
+            __syncwarp();
+            const uint32_t c0 = BPT * lane + 0 < nSlots ? st[0].excl : 0u, c1 = BPT * lane + 1 < nSlots ? st[1].excl : 0u;
+            const uint32_t c2 = BPT * lane + 2 < nSlots ? st[2].excl : 0u, c3 = BPT * lane + 3 < nSlots ? st[3].excl : 0u;
+            uint32_t incl = c0 + c1 + c2 + c3;
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl += o;
+            }
+            totalItems = __shfl_sync(FULL, incl, 31);
+            const uint32_t ex0 = incl - (c0 + c1 + c2 + c3), ex1 = ex0 + c0, ex2 = ex1 + c1, ex3 = ex2 + c2;
+            // slots past the list get excl = totalItems: they never own an item
+            st[0].excl = ex0; st[1].excl = ex1; st[2].excl = ex2; st[3].excl = ex3;
+        }
+        uint32_t *bits = sBits[warp];
+        const uint32_t leMask = 0xffffffffu >> (31 - lane);
+        const uint2 *__restrict__ tPlanes = P.t.planes, *__restrict__ qPlanes = P.q.planes;
+        int before = 0;                         // list slots that start before the round being fetched
+        int sRun = 0;                           // sum of all item scores of earlier rounds (mod 2^32)
+        for (uint32_t passBase = 0; passBase < totalItems; passBase += PASS_ITEMS) {
+            bits[lane] = 0;
+            __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 4; k++) longBits |= ((mine[k].nMisc & 0xfffffu) >= 2u * LONG_ROUND_BASES ? 1u : 0u) << k;
-        for (int k = 0; k < 4; k++) {
-            unsigned m = __ballot_sync(FULL, (longBits >> k) & 1u);
-            while (m) {
-                const int o = 4 * (__ffs(m) - 1) + k;           // block index inside the warp (uniform)
-                m &= m - 1;
-                const StageRec r = sStage[warp][o];
-                const uint32_t n = r.nMisc & 0xfffffu, misc = r.nMisc >> 20;
-                const uint32_t rounds = n / LONG_ROUND_BASES;
-                const uint32_t tSh = misc & 31u, qSh = (misc >> 5) & 31u;
-                const bool minus = (misc >> 10) & 1u, mayN = (misc >> 11) & 1u;
-                long long acc = 0;
-                for (uint32_t rd = 0; rd < rounds; rd++) {
-                    const uint32_t w = rd * 32 + lane;
-                    uint32_t t1, t0, q1, q0;
-                    loadWindow(P.t.planes, r.tW + w, tSh, t1, t0);
-                    const uint32_t qn = minus ? r.qW - w : r.qW + w;
-                    loadWindow(P.q.planes, qn, qSh, q1, q0);
-                    if (minus) { q1 = ~__brev(q1); q0 = __brev(q0); }
-                    uint32_t vmask = 0xffffffffu;
-                    int nv = 32;
-                    if (mayN) {
-                        uint32_t nt = loadNWindow(P.t.nplane, r.tW + w, tSh);
-                        uint32_t nq = loadNWindow(P.q.nplane, qn, qSh);
-                        if (minus) nq = __brev(nq);
-                        vmask = ~(nt | nq);
-                        nv = __popc(vmask);
-                    }
-                    acc += scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
-                }
-                for (int off = 16; off; off >>= 1) acc += shfl64(acc, lane ^ off);
-                if (lane == 0) {
-                    sScore[padIdx(warpV0 + o)] += acc;
-                    const uint32_t done = rounds * LONG_ROUND_BASES, rem = n - done;
-                    sStage[warp][o] = StageRec{r.tW + rounds * 32, minus ? r.qW - rounds * 32 : r.qW + rounds * 32, rem | (misc << 20),
-                                               rem ? (rem + 31) >> 5 : 1u};
-                }
-                __syncwarp();
+            for (int k = 0; k < BPT; k++) {
+                const uint32_t e = st[k].excl - passBase;
+                if (BPT * lane + k < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31));
             }
+            __syncwarp();
+            const uint32_t myWord = bits[lane];
+            __syncwarp();
+            const uint32_t passItems = totalItems - passBase < (uint32_t)PASS_ITEMS ? totalItems - passBase : (uint32_t)PASS_ITEMS;
+            const int nRounds = (int)((passItems + 31) >> 5);
+            const uint32_t idx0 = passBase + lane;
+            // A round's state: owner slot, bases left in its block from this item on (<= 0: idle lane),
+            // misc, and the four uint2 window halves.  Idle lanes (only in the list's last round) land on the
+            // last slot with left <= 0 and read padding or neighbouring words: harmless, they score 0.
+#define GAT_FETCH(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                        \
+            {                                                                                               \
+                const uint32_t heads = __shfl_sync(FULL, myWord, (R));                                      \
+                OW = before - 1 + __popc(heads & leMask);                                                   \
+                before += __popc(heads);                                                                    \
+                const StageRec rec = sStage[warp][OW];                                                      \
+                const uint32_t k = idx0 + ((uint32_t)(R) << 5) - rec.excl;                                  \
+                MISC = rec.nMisc >> 20;                                                                     \
+                LEFT = (int)(rec.nMisc & 0xfffffu) - (int)(k << 5);                                         \
+                const uint2 *tp = tPlanes + (rec.tW + k);                                                   \
+                const uint2 *qp = qPlanes + ((MISC & 0x400u) ? rec.qW - k : rec.qW + k);                    \
+                W0 = __ldg(tp); W1 = __ldg(tp + 1); W2 = __ldg(qp); W3 = __ldg(qp + 1);                     \
+            }
+#define GAT_CONSUME(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                      \
+            {                                                                                               \
+                const uint32_t tSh = MISC, qSh = MISC >> 5;                                                 \
+                const uint32_t t1 = __funnelshift_r(W0.x, W1.x, tSh), t0 = __funnelshift_r(W0.y, W1.y, tSh);\
+                uint32_t q1 = __funnelshift_r(W2.x, W3.x, qSh), q0 = __funnelshift_r(W2.y, W3.y, qSh);      \
+                const uint32_t r1 = ~__brev(q1), r0 = __brev(q0);                                           \
+                const bool minus = (MISC & 0x400u) != 0;                                                    \
+                q1 = minus ? r1 : q1; q0 = minus ? r0 : q0;                                                 \
+                int nv = LEFT > 32 ? 32 : (LEFT < 0 ? 0 : LEFT);                                            \
+                uint32_t vmask = shrOnes(32u - (uint32_t)nv);                                               \
+                if (anyN && (MISC & 0x800u) && nv) {                                                        \
+                    const StageRec rec = sStage[warp][OW];                                                  \
+                    const uint32_t k = idx0 + ((uint32_t)(R) << 5) - rec.excl;                              \
+                    uint32_t nt = loadNWindow(P.t.nplane, rec.tW + k, tSh);                                 \
+                    uint32_t nq = loadNWindow(P.q.nplane, minus ? rec.qW - k : rec.qW + k, qSh);            \
+                    if (minus) nq = __brev(nq);                                                             \
+                    vmask &= ~(nt | nq);                                                                    \
+                    nv = __popc(vmask);                                                                     \
+                }                                                                                           \
+                int x = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);                                \
+                x = scanStep(x, 1); x = scanStep(x, 2); x = scanStep(x, 4); x = scanStep(x, 8); x = scanStep(x, 16); \
+                if ((uint32_t)(LEFT - 1) < 32u) sEnd[warpV0 + OW] = sRun + x;                               \
+                sRun += __shfl_sync(FULL, x, 31);                                                           \
+            }
+            int oA, lA, oB, lB; uint32_t mA, mB; uint2 a0, a1, a2, a3, b0, b1, b2, b3;
+            GAT_FETCH(0, oA, lA, mA, a0, a1, a2, a3)
+            for (int r = 0;; r += 2) {          // software pipeline: round r+1 is in flight while round r is scored
+                if (r + 1 < nRounds) GAT_FETCH(r + 1, oB, lB, mB, b0, b1, b2, b3)
+                GAT_CONSUME(r, oA, lA, mA, a0, a1, a2, a3)
+                if (r + 1 >= nRounds) break;
+                if (r + 2 < nRounds) GAT_FETCH(r + 2, oA, lA, mA, a0, a1, a2, a3)
+                GAT_CONSUME(r + 1, oB, lB, mB, b0, b1, b2, b3)
+                if (r + 2 >= nRounds) break;
+            }
+#undef GAT_FETCH
+#undef GAT_CONSUME
         }
-    }
-    uint32_t ex0, ex1, ex2, ex3, totalItems;
-    {
         __syncwarp();
-        StageRec *st = &sStage[warp][4 * lane];
-        const uint32_t c0 = st[0].excl, c1 = st[1].excl, c2 = st[2].excl, c3 = st[3].excl;
-        uint32_t incl = c0 + c1 + c2 + c3;
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, incl, off);
-            if (lane >= off) incl += o;
-        }
-        totalItems = __shfl_sync(FULL, incl, 31);
-        ex0 = incl - (c0 + c1 + c2 + c3); ex1 = ex0 + c0; ex2 = ex1 + c1; ex3 = ex2 + c2;
-        st[0].excl = ex0; st[1].excl = ex1; st[2].excl = ex2; st[3].excl = ex3;
-        __syncwarp();
-    }
-    {
-        // Software pipeline: the loads of round r+1 are issued before round r is scored, so two
-        // rounds of genome windows are in flight per warp.
-        // A round's state: heads (bit i = a block starts at lane i), owner (block of this lane's
-        // item), meta = valid bases (6 bits) | misc << 6, and the four uint2 window halves.
-        auto fetch = [&](uint32_t base, int before, unsigned &heads, int &owner, uint32_t &meta,
-                         uint2 &ta, uint2 &tb, uint2 &qa, uint2 &qb) {
-            heads = __reduce_or_sync(FULL, shl1(ex0 - base) | shl1(ex1 - base) | shl1(ex2 - base) | shl1(ex3 - base));
-            owner = before - 1 + __popc(heads & (0xffffffffu >> (31 - lane)));
-            meta = 0;
-            ta = tb = qa = qb = make_uint2(0, 0);
-            if (base + lane < totalItems) {
-                const StageRec r = sStage[warp][owner];
-                const uint32_t k = base + lane - r.excl, misc = r.nMisc >> 20;
-                const int left = (int)(r.nMisc & 0xfffffu) - (int)(k << 5);
-                if (left > 0) {
-                    meta = (uint32_t)(left >= 32 ? 32 : left) | (misc << 6);
-                    const uint2 *tp = P.t.planes + (r.tW + k);
-                    const uint2 *qp = P.q.planes + ((misc >> 10) & 1u ? r.qW - k : r.qW + k);
-                    ta = __ldg(tp); tb = __ldg(tp + 1); qa = __ldg(qp); qb = __ldg(qp + 1);
-                }
-            }
-        };
-        int before = 0;                         // blocks that start before the current round
-        unsigned hA; int oA; uint32_t mA; uint2 a0, a1, a2, a3;
-        if (totalItems) fetch(0, 0, hA, oA, mA, a0, a1, a2, a3);
-        for (uint32_t base = 0; base < totalItems; base += 32) {
-            unsigned hB = 0; int oB = 0; uint32_t mB = 0; uint2 b0, b1, b2, b3;
-            b0 = b1 = b2 = b3 = make_uint2(0, 0);
-            const int beforeNext = before + __popc(hA);
-            if (base + 32 < totalItems) fetch(base + 32, beforeNext, hB, oB, mB, b0, b1, b2, b3);
-            int s = 0;
-            int nv = (int)(mA & 63u);
-            if (nv) {
-                const uint32_t misc = mA >> 6, tSh = misc & 31u, qSh = (misc >> 5) & 31u;
-                const bool minus = (misc >> 10) & 1u;
-                uint32_t vmask = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
-                const uint32_t t1 = __funnelshift_r(a0.x, a1.x, tSh), t0 = __funnelshift_r(a0.y, a1.y, tSh);
-                uint32_t q1 = __funnelshift_r(a2.x, a3.x, qSh), q0 = __funnelshift_r(a2.y, a3.y, qSh);
-                if (minus) { q1 = ~__brev(q1); q0 = __brev(q0); }   // reverse, complement = flip bit1
-                if (anyN && ((misc >> 11) & 1u)) {
-                    const StageRec r = sStage[warp][oA];
-                    const uint32_t k = base + lane - r.excl;
-                    uint32_t nt = loadNWindow(P.t.nplane, r.tW + k, tSh);
-                    uint32_t nq = loadNWindow(P.q.nplane, minus ? r.qW - k : r.qW + k, qSh);
-                    if (minus) nq = __brev(nq);
-                    vmask &= ~(nt | nq);            // N scores 0 against everything (axt.c:431-454)
-                    nv = __popc(vmask);
-                }
-                s = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
-            }
-            // hand the 32 partial sums to the blocks that own them
-            if ((hA >> 1) == 0) {           // one block owns this whole round (long block): warp reduce
-                const int tot = __reduce_add_sync(FULL, s);
-                if (lane == 0) sScore[padIdx(warpV0 + before - 1 + (int)(hA & 1u))] += tot;
-            } else if (base + lane < totalItems) {
-                atomicAdd(&sAcc[warp][oA], s);      // <= 2 such rounds per block: no 32-bit overflow (|M| <= 2^19)
-            }
-            before = beforeNext;
-            hA = hB; oA = oB; mA = mB; a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+        // a slot's items summed to sEnd[slot] - sEnd[slot - 1]: add that to its block's score
+        {
+            const int4 e4 = *reinterpret_cast<const int4 *>(&sEnd[warpV0 + BPT * lane]);
+            int prevEnd = __shfl_up_sync(FULL, e4.w, 1);
+            if (lane == 0) prevEnd = 0;
+            const int d[BPT] = {e4.x - prevEnd, e4.y - e4.x, e4.z - e4.y, e4.w - e4.z};
+#pragma unroll
+            for (int k = 0; k < BPT; k++)
+                if (BPT * lane + k < nSlots) sScore[warpV0 + sSlotV[warpV0 + BPT * lane + k]] += d[k];
         }
     }
     __syncwarp();
@@ -717,21 +753,21 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     // of the warp, one warp scan joins the lanes; what crosses warps is resolved by whichever warp
     // of the CTA finishes last (no CTA-wide barrier: warps retire at their own pace).
     {
-        // 32-bit tuples if every partial sum of this warp's blocks stays below 2^28
+        const int4 a4 = *reinterpret_cast<const int4 *>(&sScore[warpV0 + BPT * lane]);
+        const int4 g4 = *reinterpret_cast<const int4 *>(&sGap[warpV0 + BPT * lane]);
+        const uint32_t fl4 = *reinterpret_cast<const uint32_t *>(&sFlag[warpV0 + BPT * lane]);
+        const int a[BPT] = {a4.x, a4.y, a4.z, a4.w};
+        const int g[BPT] = {g4.x, g4.y, g4.z, g4.w};
+        // 32-bit tuples if every partial sum of this warp's blocks stays below 2^27
         long long mag = 0;
-        const int p0 = padIdx(warpV0 + 4 * lane);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const long long a = sScore[p0 + k] + sAcc[warp][4 * lane + k];
-            sScore[p0 + k] = a;
-            const long long g = sGap[p0 + k];
-            mag += (a < 0 ? -a : a) + (g < 0 ? -g : g);
-        }
-        const bool small = __all_sync(FULL, mag < (1LL << 23));
-        const unsigned long long chunkEnd = total < vb0 + CHUNK ? total : vb0 + CHUNK;
-        if (small) warpJobReduce<int>(P, sScore, sGap, sFlag, sJob, warpV0, vb0, chunkEnd, warp, lane,
+        for (int k = 0; k < BPT; k++) mag += (long long)(a[k] < 0 ? -(long long)a[k] : (long long)a[k]) + (g[k] < 0 ? -(long long)g[k] : (long long)g[k]);
+        const bool small = __all_sync(FULL, mag < (1LL << 22));
+        const int wsel = warp * BPT + (lane >> 3);          // bitmap word of my four blocks
+        const uint32_t myWr = __shfl_sync(FULL, wrank, wsel), myHw = sHead[wsel];
+        if (small) warpJobReduce<int>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
                                       sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
-        else warpJobReduce<long long>(P, sScore, sGap, sFlag, sJob, warpV0, vb0, chunkEnd, warp, lane,
+        else warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
                                       sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
     }
     // last warp of the CTA to get here stitches the warps together
@@ -749,7 +785,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             const Tup fin = tupCombine(c, sWarpPend[w]);
             if (ch) {
                 P.outGlobal[sWarpPendJob[w]] = fin.d;
-                P.outLocal[sWarpPendJob[w]] = max64(0, max64(fin.e, fin.f));
+                P.outLocal[sWarpPendJob[w]] = finalLocal(fin);
             } else P.chunkHead[blockIdx.x] = fin;       // job began in an earlier chunk and ends here
         }
         if (sWarpHead[w]) { c = sWarpAgg[w]; ch = true; }
@@ -764,16 +800,16 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
 // ------------------------------------------------------------------ cross-chunk fix-up
 // A job that starts in chunk c and ends in chunk c' > c:  tail(c) + head(c+1) + ... + head(c').
 // One warp per chunk that has such a tail; lanes fold contiguous slices, then an ordered fold.
-__global__ void fixupKernel(const gat_job *__restrict__ jobs, unsigned long long nJobs, unsigned long long total,
+__global__ void fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned long long total,
                             const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
                             const int *__restrict__ chunkTailJob, uint32_t nChunks,
-                            long long *__restrict__ outGlobal, long long *__restrict__ outLocal)
+                            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, const int *__restrict__ err)
 {
     uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= nChunks) return;
+    if (c >= nChunks || *err) return;
     const int j = chunkTailJob[c];
     if (j < 0) return;
-    const unsigned long long np = ((unsigned long long)j + 1 < nJobs) ? (unsigned long long)jobs[j + 1].blockPtr : total;
+    const unsigned long long np = info[j + 1].blockPtr;
     const uint32_t cLast = (uint32_t)((np - 1) / CHUNK);
     const uint32_t count = cLast - c;                  // heads to fold: chunks c+1 .. cLast
     const uint32_t per = (count + 31) / 32;
@@ -789,7 +825,7 @@ __global__ void fixupKernel(const gat_job *__restrict__ jobs, unsigned long long
     }
     if (lane == 0) {
         outGlobal[j] = all.d;
-        outLocal[j] = max64(0, max64(all.e, all.f));
+        outLocal[j] = finalLocal(all);
     }
 }
 

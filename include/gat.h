@@ -43,7 +43,9 @@ extern "C" {
 #define GAT_BLOCK_JOINED 0x80000000u/* gat_block.size bit: this record continues the previous record's
                                      * gapless block (a long block split by the host for load
                                      * balance): no gap cost, no local-score clamp between them */
-#define GAT_MAX_BLOCK_BASES ((1u << 20) - 1) /* largest gat_block.size the kernels accept */
+#define GAT_MAX_BLOCK_BASES ((1u << 20) - 1) /* largest gat_block.size the kernels accept; with matrix entries beyond
+                                             * +-2047 the limit drops to (2^31-1)/max|M| (32-bit record sums), never
+                                             * below GAT_SPLIT_BASES: see gat_max_record_bases() */
 #define GAT_SPLIT_BASES 4096u                /* recommended record size: hosts cut longer gapless blocks into
                                              * JOINED records of this many bases so that a few very long blocks
                                              * spread over many warps (gathost::buildRecords does) */
@@ -128,6 +130,8 @@ int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, uint64_t pack
                     const gat_nrun *nRuns, uint64_t nNRuns);
 
 int gat_set_scoring(gat_ctx *ctx, const gat_scoring *scoring);
+/* Longest record (gat_block.size) gat_score accepts under the current scoring parameters. */
+uint32_t gat_max_record_bases(const gat_ctx *ctx);
 
 /* The hot call.  Host arrays in, host arrays out, blocking.  `totalJobBlocks` closes the CSR
  * (= blockPtr of a virtual job nJobs).  global[j] = chainCalcScore, local[j] =

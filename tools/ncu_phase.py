@@ -40,7 +40,7 @@ marks = [('tuple helpers', 'struct Tup {', 'struct GapView'), ('gap cost', '// -
          ('window loads', '// ------------------------------------------------------------------ base windows', '// does [g0, g0+len) touch'),
          ('mayTouchN', '// does [g0, g0+len) touch', '// ------------------------------------------------------------------ 32 base pairs'),
          ('scoreWindow', '// ------------------------------------------------------------------ 32 base pairs', '// ------------------------------------------------------------------ chunk index'),
-         ('clip/load helpers', '// chainFastSubsetOnT clip (chain.c:513-522) of one record', 'scoreChunksKernel(const __grid_constant__'),
+         ('phase3 reduce fn', '// Phase 3 of scoreChunksKernel for one warp', 'scoreChunksKernel(const __grid_constant__'),
          ('staging+phase0', 'scoreChunksKernel(const __grid_constant__', '// ---- phase 1'),
          ('phase1 descriptors', '// ---- phase 1', '// ---- phase 2'), ('phase2 items', '// ---- phase 2', '// ---- phase 3'),
          ('phase3', '// ---- phase 3', '// ------------------------------------------------------------------ cross-chunk fix-up')]
