@@ -341,6 +341,16 @@ def main():
         kms.append(sc.stats()["score_kernel_ms"])
     sc.set_profiling(False)
     kernel_ms = float(np.mean(kms))
+    if os.environ.get("GAT_TIMING"):      # debug build (-DGAT_TIMING): clocks per phase, averaged per warp
+        import ctypes
+        from genomealignmenttools_b200 import _native
+        lib = _native.load()
+        out = (ctypes.c_uint64 * 8)()
+        lib.gat_debug_timing(out)
+        wl.run(); sc.synchronize()
+        lib.gat_debug_timing(out)
+        warps = ((w.total + 1023) // 1024) * 8
+        sys.stderr.write("phase clocks per warp: " + " ".join("%d" % (x // warps) for x in out) + "\n")
 
     # ---- end-to-end through the public call with pinned host buffers (e2e)
     pj, pb = PinnedArray(len(w.jobs), JOB_DTYPE), PinnedArray(len(w.blocks), BLOCK_DTYPE)

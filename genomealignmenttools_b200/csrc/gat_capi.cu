@@ -146,8 +146,10 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
     GenomeDev &g = ctx->genome[side];
     g.release();
 
-    // host-side layout: every sequence starts on a 128-base group boundary
-    std::vector<long long> base(nSeq);
+    // host-side layout: every sequence starts on a 128-base group boundary; the query is followed by a
+    // reverse-complement image of each of its sequences (index nSeq + i), built on the device below
+    const uint32_t nImages = side == GAT_QUERY ? 2 * nSeq : nSeq;
+    std::vector<long long> base(nImages);
     std::vector<unsigned long long> wordStart(nSeq + 1);
     long long cursor = (long long)PAD_FRONT_GROUPS * GROUP_BASES;
     unsigned long long words = 0;
@@ -161,6 +163,10 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
         cursor += (long long)(((unsigned long long)seqSize[i] + GROUP_BASES - 1) / GROUP_BASES) * GROUP_BASES;
     }
     wordStart[nSeq] = words;
+    for (uint32_t i = nSeq; i < nImages; i++) {
+        base[i] = cursor;
+        cursor += (long long)(((unsigned long long)seqSize[i - nSeq] + GROUP_BASES - 1) / GROUP_BASES) * GROUP_BASES;
+    }
     const long long totalBases = cursor + (long long)PAD_BACK_GROUPS * GROUP_BASES;
     if ((unsigned long long)totalBases >> 5 >= 0x7fffffffull)
         return fail(GAT_EINVAL, "gat_load_genome: genome of %lld bases exceeds the 2^36-base layout limit", totalBases);
@@ -199,7 +205,7 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
     CUG(cudaMalloc(&g.planes, planeWords * 4));
     CUG(cudaMalloc(&g.nplane, nWords * 4));
     CUG(cudaMalloc(&g.nwin, winWords * 4));
-    CUG(cudaMalloc(&g.seqBase, nSeq * sizeof(long long)));
+    CUG(cudaMalloc(&g.seqBase, nImages * sizeof(long long)));
     CUG(cudaMalloc(&g.seqSize, nSeq * sizeof(uint32_t)));
     CUG(cudaMalloc(&dRaw, packedBytes + 16));
     CUG(cudaMalloc(&dByteOff, nSeq * sizeof(unsigned long long)));
@@ -211,7 +217,7 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
     CUG(cudaMemcpyAsync(dRaw, packed, packedBytes, cudaMemcpyHostToDevice, st));
     CUG(cudaMemcpyAsync(dByteOff, seqByteOffset, nSeq * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUG(cudaMemcpyAsync(dWordStart, wordStart.data(), (nSeq + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    CUG(cudaMemcpyAsync(g.seqBase, base.data(), nSeq * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUG(cudaMemcpyAsync(g.seqBase, base.data(), nImages * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUG(cudaMemcpyAsync(g.seqSize, seqSize, nSeq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     if (words) {
         unsigned long long grid = (words + 255) / 256;
@@ -223,6 +229,11 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
         CUG(cudaMemcpyAsync(dRuns, runs.data(), runs.size() * sizeof(gat_nrun), cudaMemcpyHostToDevice, st));
         unsigned long long grid = (runs.size() * 32 + 255) / 256;
         nRunKernel<<<(unsigned)grid, 256, 0, st>>>(dRuns, runs.size(), g.seqBase, g.nplane, g.nwin);
+        CUG(cudaGetLastError());
+    }
+    if (side == GAT_QUERY && words) {
+        unsigned long long grid = (words + 255) / 256;
+        revCompKernel<<<(unsigned)grid, 256, 0, st>>>(g.seqSize, g.seqBase, dWordStart, nSeq, words, g.planes, g.nplane, g.nwin);
         CUG(cudaGetLastError());
     }
     CUG(cudaStreamSynchronize(st));
@@ -527,6 +538,18 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
 }
 
 extern "C" uint32_t gat_max_record_bases(const gat_ctx *ctx) { return ctx ? ctx->maxBlockBases : 0; }
+
+#ifdef GAT_TIMING
+// debug builds: clocks per phase summed over all warps since the last call
+extern "C" int gat_debug_timing(unsigned long long *out8)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, gat::gTiming, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(gat::gTiming, z, sizeof z);
+    return 0;
+}
+#endif
 
 extern "C" int gat_synchronize(gat_ctx *ctx)
 {

@@ -113,7 +113,7 @@ struct GapView {           // tables of struct gapCalc (gapCalc.c:12-37) as the 
 // A job as the scoring kernel reads it (written by jobPrepKernel): one 32-byte sector.
 struct __align__(16) JobInfo {
     uint32_t tBaseW, qBaseW;    // index of the 32-base word that holds base 0 of the target / query sequence
-    uint32_t tSize, qSizeStrand;// sequence sizes; bit 31 of the latter = query on the '-' strand
+    uint32_t tSize, qSize;      // sequence sizes.  A '-' job's qBaseW is that of the reverse-complement copy of the query sequence
     int32_t clipStart, clipEnd;
     uint32_t delta;             // firstBlock - blockPtr (mod 2^32): record index = job-block index + delta
     uint32_t blockPtr;
@@ -188,6 +188,15 @@ __device__ __forceinline__ int gapCost(const GapView &g, const int *small, const
     return gapCostExact(g, small, longPos, longVal, which, v);
 }
 
+__device__ __forceinline__ int gapCostOf(const GapView &g, const int *small, const int *__restrict__ dense,
+                                         const int *longPos, const double *longVal, uint32_t which, uint32_t v)
+{
+    if ((int)v < 0) return INT32_MIN;                 // dq+dt overflowed int (undefined in the reference)
+    if (v < (uint32_t)g.smallSize) return small[which * g.smallSize + v];
+    if (v < (uint32_t)g.denseSize) return __ldg(dense + (size_t)which * g.denseSize + v);
+    return gapCostExact(g, small, longPos, longVal, (int)which, (int)v);
+}
+
 __global__ void gapDenseKernel(GapView g, const int *__restrict__ small, const int *__restrict__ longPos,
                                const double *__restrict__ longVal, int *__restrict__ dense)
 {
@@ -234,16 +243,26 @@ __device__ __forceinline__ uint32_t loadNWindow(const uint32_t *__restrict__ np,
 }
 
 // do the 32-base words wFirst..wLast touch a 256-base window (8 words) that contains N?
+__device__ __noinline__ bool wordsTouchNLong(const uint32_t *__restrict__ nwin, uint32_t word0, uint32_t word1, uint32_t loMask, uint32_t hiMask)
+{
+    if (__ldg(nwin + word0) & loMask) return true;
+    for (uint32_t word = word0 + 1; word < word1; word++)
+        if (__ldg(nwin + word)) return true;
+    return (__ldg(nwin + word1) & hiMask) != 0;
+}
 __device__ __forceinline__ bool wordsTouchN(const uint32_t *__restrict__ nwin, uint32_t wFirst, uint32_t wLast)
 {
     const uint32_t w0 = wFirst >> 3, w1 = wLast >> 3;
     const uint32_t word0 = w0 >> 5, word1 = w1 >> 5;
     const uint32_t loMask = 0xffffffffu << (w0 & 31), hiMask = 0xffffffffu >> (31 - (w1 & 31));
     if (word0 == word1) return (__ldg(nwin + word0) & loMask & hiMask) != 0;     // blocks under 8 kb
-    if (__ldg(nwin + word0) & loMask) return true;
-    for (uint32_t word = word0 + 1; word < word1; word++)
-        if (__ldg(nwin + word)) return true;
-    return (__ldg(nwin + word1) & hiMask) != 0;
+    return wordsTouchNLong(nwin, word0, word1, loMask, hiMask);
+}
+// valid-base mask of one 32-base window pair when N may be present (cold)
+__device__ __noinline__ uint32_t nFreeMask(const uint32_t *__restrict__ tn, uint32_t tW, uint32_t tSh,
+                                           const uint32_t *__restrict__ qn, uint32_t qW, uint32_t qSh)
+{
+    return ~(loadNWindow(tn, tW, tSh) | loadNWindow(qn, qW, qSh));      // N scores 0 against everything (axt.c:431-454)
 }
 
 // ------------------------------------------------------------------ 32 base pairs -> score
@@ -300,10 +319,10 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
                               long long *__restrict__ outGlobal, long long *__restrict__ outLocal, int *__restrict__ err)
 {
     const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > nJobs) return;
     JobInfo o;
-    o.tBaseW = o.qBaseW = o.tSize = o.qSizeStrand = 0; o.clipStart = o.clipEnd = 0; o.delta = 0;
+    o.tBaseW = o.qBaseW = o.tSize = o.qSize = 0; o.clipStart = o.clipEnd = 0; o.delta = 0;
     o.blockPtr = (uint32_t)total;                       // sentinel record nJobs closes the CSR
+    unsigned long long c0 = 0, c1 = 0;                  // chunks [c0, c1) start inside this job
     if (j < nJobs) {
         const gat_job job = loadJob(jobs, (uint32_t)j);
         const unsigned long long bp = job.blockPtr;
@@ -318,29 +337,47 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
             if (np > bp) e |= ERR_SEQ;                  // sizes stay 0: every block of the job fails its range check
         } else {
             o.tBaseW = (uint32_t)(__ldg(tSeqBase + job.tSeq) >> 5);
-            o.qBaseW = (uint32_t)(__ldg(qSeqBase + qSeq) >> 5);
+            // the query buffer holds every sequence twice: forward (index s) and reverse-complemented (qNSeq + s)
+            o.qBaseW = (uint32_t)(__ldg(qSeqBase + ((job.qSeq >> 31) ? qNSeq + qSeq : qSeq)) >> 5);
             o.tSize = __ldg(tSeqSize + job.tSeq);
-            o.qSizeStrand = __ldg(qSeqSize + qSeq) | (job.qSeq & 0x80000000u);
+            o.qSize = __ldg(qSeqSize + qSeq);
         }
         if (e) atomicOr(err, e);
         if (np <= bp) { outGlobal[j] = 0; outLocal[j] = 0; }
-        else if (!(e & ERR_CSR))
-            for (unsigned long long c = (bp + CHUNK - 1) / CHUNK; c * CHUNK < np && c < nChunks; c++) chunkJob[c] = (uint32_t)j;
+        else if (!(e & ERR_CSR)) {
+            c0 = (bp + CHUNK - 1) / CHUNK;
+            c1 = (np + CHUNK - 1) / CHUNK;
+            if (c1 > nChunks) c1 = nChunks;
+        }
     }
+    // chunkJob: a job that covers a few chunk boundaries writes them itself, the warp shares the long ones
+    const unsigned lane = threadIdx.x & 31;
+    const bool wide = c1 > c0 + 4;
+    if (!wide) for (unsigned long long c = c0; c < c1; c++) chunkJob[c] = (uint32_t)j;
+    for (unsigned m = __ballot_sync(FULL, wide); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const unsigned long long b0 = __shfl_sync(FULL, c0, src), b1 = __shfl_sync(FULL, c1, src);
+        const uint32_t jj = (uint32_t)__shfl_sync(FULL, j, src);
+        for (unsigned long long c = b0 + lane; c < b1; c += 32) chunkJob[c] = jj;
+    }
+    if (j > nJobs) return;
     uint4 *dst = reinterpret_cast<uint4 *>(info + j);
-    dst[0] = make_uint4(o.tBaseW, o.qBaseW, o.tSize, o.qSizeStrand);
+    dst[0] = make_uint4(o.tBaseW, o.qBaseW, o.tSize, o.qSize);
     dst[1] = make_uint4((uint32_t)o.clipStart, (uint32_t)o.clipEnd, o.delta, o.blockPtr);
 }
 
 // ------------------------------------------------------------------ the scoring kernel
-// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | minus<<10 | mayN<<11; excl: items of the warp before this block
+// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | mayN<<11; excl: items of the warp before this block
 struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 
 #ifndef GAT_MIN_CTAS
 #define GAT_MIN_CTAS 5
 #endif
 #ifndef GAT_P1_UNROLL
-#define GAT_P1_UNROLL 2
+#define GAT_P1_UNROLL 1
+#endif
+#ifndef GAT_PASSB_PAIR
+#define GAT_PASSB_PAIR 0
 #endif
 #ifndef GAT_PREFETCH
 #define GAT_PREFETCH 1      // bit 0: first genome sectors of each block, from phase 1
@@ -354,7 +391,7 @@ __device__ __forceinline__ JobInfo loadInfo(const JobInfo *__restrict__ info, ui
     const uint4 *p = reinterpret_cast<const uint4 *>(info + j);
     const uint4 a = __ldg(p), b = __ldg(p + 1);
     JobInfo r;
-    r.tBaseW = a.x; r.qBaseW = a.y; r.tSize = a.z; r.qSizeStrand = a.w;
+    r.tBaseW = a.x; r.qBaseW = a.y; r.tSize = a.z; r.qSize = a.w;
     r.clipStart = (int)b.x; r.clipEnd = (int)b.y; r.delta = b.z; r.blockPtr = b.w;
     return r;
 }
@@ -449,10 +486,30 @@ __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&
     }
 }
 
+#ifdef GAT_TIMING
+__device__ unsigned long long gTiming[8];   // sum over warps of clocks spent per phase (debug builds)
+#define GAT_TICK(i) { const long long now_ = clock64(); if (lane == 0) atomicAdd(&gTiming[i], (unsigned long long)(now_ - tick_)); tick_ = now_; }
+#else
+#define GAT_TICK(i)
+#endif
+
+// the 64-bit form is rare (a warp whose 128 blocks sum past 2^27): keep it out of the hot instruction stream
+__device__ __noinline__ void warpJobReduceWide(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
+                                               uint32_t myWr, uint32_t myHw, const uint32_t *sJobSlot, int warpV0, int vEnd,
+                                               int warp, int lane, Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead,
+                                               int *sWarpPendJob, int *sLastIsEnd, uint32_t *sLastJob)
+{
+    warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane, sWarpAgg, sWarpPend, sWarpHead,
+                             sWarpPendJob, sLastIsEnd, sLastJob);
+}
+
 template <bool SYM>
 __global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
 scoreChunksKernel(const __grid_constant__ ScoreParams P)
 {
+#ifdef GAT_TIMING
+    long long tick_ = clock64();
+#endif
     __shared__ uint32_t sHead[CHUNK / 32 + 1];  // bit v: a job starts at job-block v of the chunk (bit 0: always; bit vEnd: end of list)
     __shared__ uint32_t sJobSlot[CHUNK + 1];    // job index of the r-th head
     __shared__ __align__(16) int sGap[CHUNK];   // cost of the gap in front of the block
@@ -526,119 +583,222 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     }
     __syncthreads();
 
-    // ---- phase 1: this warp's TILE job-blocks, 32 at a time: load + clip the records, gap costs,
-    // item counts.  Block v = warp*TILE + sub*32 + lane.
+    GAT_TICK(0)
+    // ---- phase 1: this warp's TILE job-blocks, 32 at a time; block v = warp*TILE + sub*32 + lane.
+    // Pass A1 puts the record loads of all four sub-tiles in flight at once (one DRAM round trip per warp,
+    // not four); pass A2 turns records into window descriptors and asks L2 for the first and last sector of
+    // every window; pass B then scores each block's first 32 bases out of L2 and builds the item list.
     bool anyN = false;
     int nSlots = 0;                     // blocks of this warp with more than 32 bases: they get a slot in the item list
-    int carryTe = 0, carryQe = 0;       // clipped ends of the previous sub-tile's last block
-#pragma unroll P1_UNROLL
-    for (int sub = 0; sub < BPT; sub++) {
-        const int wi = warp * BPT + sub;
-        const int v = wi * 32 + lane;
-        const uint32_t hw = sHead[wi], hwn = sHead[wi + 1];
-        const uint32_t wr = __shfl_sync(FULL, wrank, wi);
-        const bool valid = v < vEnd;
-        uint32_t tW = 0, qW = 0, n = 0, misc = 0;
-        unsigned char flag = 0;
-        int ts = 0, qs = 0, len = 0;
-        bool joined = false;
-        JobInfo job;
-        job.tBaseW = job.qBaseW = job.tSize = job.qSizeStrand = job.delta = job.blockPtr = 0; job.clipStart = job.clipEnd = 0;
-        uint32_t bi = 0;
-        if (valid) {
-            const uint32_t rank = wr + __popc(hw & (0xffffffffu >> (31 - lane))) - 1;
-            job = loadInfo(P.info, sJobSlot[rank]);
-            flag = 8;
-            if (v == 0 ? sFirstIsHead != 0 : ((hw >> lane) & 1u) != 0) flag |= 1;
-            if (lane < 31 ? ((hw >> (lane + 1)) & 1u) != 0 : (hwn & 1u) != 0) flag |= 2;
-            bi = vb0 + (uint32_t)v + job.delta;
-            if ((unsigned long long)bi >= P.nBlocks) { atomicOr(P.err, ERR_BLOCKIDX); }
-            else {
-                clipBlock(loadBlock(P.blocks, bi), job.clipStart, job.clipEnd, ts, qs, len, joined);
-                const int nn = len > 0 ? len : 0;
-                const uint32_t tSize = job.tSize, qSize = job.qSizeStrand & 0x7fffffffu;
-                const bool minus = (job.qSizeStrand >> 31) != 0;
-                if (nn > 0 && (ts < 0 || qs < 0 || (unsigned)ts + (unsigned)nn > tSize || (unsigned)qs + (unsigned)nn > qSize)) {
-                    atomicOr(P.err, ERR_COORD);
-                } else if ((uint32_t)nn > P.maxBlockBases) {
-                    atomicOr(P.err, ERR_TOOLONG);
-                } else if (nn > 0) {
-                    n = (uint32_t)nn;
-                    // '+': first base of the block.  '-': one past the block's last base in forward
-                    // coordinates; rc position p is forward position qSize-1-p (dnautil.c:466-470).
-                    const uint32_t qAt = minus ? qSize - (uint32_t)qs : (uint32_t)qs;      // local coordinate
-                    const uint32_t qLo = minus ? qAt - n : qAt;
-                    const uint32_t tSh = (uint32_t)ts & 31u, qSh = qAt & 31u;
-                    tW = job.tBaseW + ((uint32_t)ts >> 5);
-                    qW = minus ? job.qBaseW + (uint32_t)(((int)qAt - 32) >> 5) : job.qBaseW + (qAt >> 5);
-                    const bool mayN = wordsTouchN(P.t.nwin, tW, tW + ((tSh + n - 1) >> 5)) ||
-                                      wordsTouchN(P.q.nwin, job.qBaseW + (qLo >> 5), job.qBaseW + ((qLo + n - 1) >> 5));
-                    misc = tSh | (qSh << 5) | (minus ? 1u << 10 : 0u) | (mayN ? 1u << 11 : 0u);
-                    anyN |= mayN;
-#if GAT_PREFETCH & 1
-                    // phase 2 reads the rest of the block a few microseconds from now: pull its last sector into L2
-                    if (n > 32) {
-                        const uint32_t lastItem = (n - 1) >> 5;
-                        prefetchL2(P.t.planes + tW + lastItem);
-                        prefetchL2(P.q.planes + (minus ? qW - lastItem : qW + lastItem + 1));
-                    }
-#endif
+    const uint32_t leMask = 0xffffffffu >> (31 - lane);
+    {
+        uint32_t jOf[BPT];
+        gat_block rec[BPT];
+        uint32_t okBits = 0;            // bit sub: my block of that sub-tile exists and its record index is in range
+        gat_block prevRec;              // lane 0: the record in front of the warp's first block
+        bool badIdx = false;
+#pragma unroll
+        for (int sub = 0; sub < BPT; sub++) {
+            const int wi = warp * BPT + sub;
+            const int v = wi * 32 + lane;
+            const uint32_t hw = sHead[wi];
+            const uint32_t wr = __shfl_sync(FULL, wrank, wi);
+            const bool valid = v < vEnd;
+            const uint32_t rank = wr + __popc(hw & leMask) - 1;
+            jOf[sub] = valid ? sJobSlot[rank] : j0;
+            const uint32_t bi = vb0 + (uint32_t)v + __ldg(&P.info[jOf[sub]].delta);
+            const bool ok = valid && (unsigned long long)bi < P.nBlocks;
+            badIdx |= valid && !ok;
+            okBits |= ok ? 1u << sub : 0u;
+            rec[sub] = loadBlock(P.blocks, ok ? bi : 0u);
+            if (sub == 0) prevRec = loadBlock(P.blocks, ok && bi > 0 ? bi - 1 : 0u);
+        }
+        int carryTe = 0, carryQe = 0;   // clipped ends of the previous sub-tile's last block
+        int errAcc = badIdx ? ERR_BLOCKIDX : 0;
+        // straight-line code (selects, no branches) so that the four unrolled sub-tiles interleave
+#pragma unroll
+        for (int sub = 0; sub < BPT; sub++) {
+            const int wi = warp * BPT + sub;
+            const int v = wi * 32 + lane;
+            const uint32_t hw = sHead[wi], hwn = sHead[wi + 1];
+            const bool ok = (okBits >> sub) & 1u;
+            const JobInfo job = loadInfo(P.info, jOf[sub]);     // its line came in with delta
+            const bool isHead = v == 0 ? sFirstIsHead != 0 : ((hw >> lane) & 1u) != 0;
+            const bool isEnd = ((lane < 31 ? hw >> (lane + 1) : hwn) & 1u) != 0;
+            uint32_t flag = v < vEnd ? (8u | (isHead ? 1u : 0u) | (isEnd ? 2u : 0u)) : 0u;
+            // chainFastSubsetOnT clip (chain.c:513-522)
+            const bool joined = (rec[sub].size & GAT_BLOCK_JOINED) != 0;
+            int ts = rec[sub].tStart, qs = rec[sub].qStart;
+            int te = ts + (int)(rec[sub].size & 0x7fffffffu);
+            const int cut = job.clipStart > ts ? job.clipStart - ts : 0;
+            ts += cut; qs += cut;
+            te = te > job.clipEnd ? job.clipEnd : te;
+            const int len = te - ts;
+            const int nn = len > 0 ? len : 0;
+            const bool bad = nn > 0 && (ts < 0 || qs < 0 || (unsigned)ts + (unsigned)nn > job.tSize || (unsigned)qs + (unsigned)nn > job.qSize);
+            const bool tooLong = (uint32_t)nn > P.maxBlockBases;
+            errAcc |= ok && bad ? ERR_COORD : 0;
+            errAcc |= ok && !bad && tooLong ? ERR_TOOLONG : 0;
+            // a '-' job points at the reverse-complement copy of its query sequence, whose coordinates
+            // are the chain's own (chainFormat.doc): both strands read forward from here on
+            const uint32_t n = ok && !bad && !tooLong ? (uint32_t)nn : 0u;
+            const uint32_t tW = n ? job.tBaseW + ((uint32_t)ts >> 5) : 0u;
+            const uint32_t qW = n ? job.qBaseW + ((uint32_t)qs >> 5) : 0u;
+            const uint32_t misc = ((uint32_t)ts & 31u) | (((uint32_t)qs & 31u) << 5);
+            // ask L2 for the first and the last sector of both windows (the same one for most blocks)
+            prefetchL2(P.t.planes + tW);
+            prefetchL2(P.q.planes + qW);
+            prefetchL2(P.t.planes + tW + ((((uint32_t)ts & 31u) + n) >> 5));
+            prefetchL2(P.q.planes + qW + ((((uint32_t)qs & 31u) + n) >> 5));
+            // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
+            // last block, or the record fetched for that purpose when this is the warp's first sub-tile
+            const int cte = ok ? te : 0, cqe = ok ? qs + len : 0;
+            int pte = __shfl_up_sync(FULL, cte, 1), pqe = __shfl_up_sync(FULL, cqe, 1);
+            if (sub == 0) {
+                int pts, pqs, plen; bool pj;
+                clipBlock(prevRec, job.clipStart, job.clipEnd, pts, pqs, plen, pj);
+                carryTe = pts + plen; carryQe = pqs + plen;
+            }
+            pte = lane == 0 ? carryTe : pte; pqe = lane == 0 ? carryQe : pqe;
+            carryTe = __shfl_sync(FULL, cte, 31); carryQe = __shfl_sync(FULL, cqe, 31);
+            // gap in front of the block, as (table, size): gapCalcCost's choice of table (gapCalc.c:304-330);
+            // the look-up itself waits for pass B
+            int dq = qs - pqe, dt = ts - pte;
+            dt = dt < 0 ? 0 : dt;
+            dq = dq < 0 ? 0 : dq;
+            const uint32_t which = dt == 0 ? 0u : (dq == 0 ? 1u : 2u);
+            const bool gapped = ok && !isHead && !joined;
+            const uint32_t gapV = gapped ? (uint32_t)dq + (uint32_t)dt : 0u;      // one of them is 0 unless which == 2
+            flag |= ok && !isHead && joined ? 4u : 0u;
+            flag |= gapped ? which << 4 : 0u;
+            sFlag[v] = (unsigned char)flag;
+            sStage[warp][sub * 32 + lane] = StageRec{tW, qW, n | (misc << 20), gapV};
+        }
+        if (errAcc) atomicOr(P.err, errAcc);
+    }
+#if GAT_PASSB_PAIR
+    // pass B, two sub-tiles at a time in straight-line code: loads of both first, rare cases last
+#pragma unroll 1
+    for (int sp = 0; sp < BPT; sp += 2) {
+        StageRec d[2];
+        uint2 ta[2], tb[2], qa[2], qb[2];
+        uint32_t tN[2], qN[2], flag[2];
+        int gDense[2];
+        bool slow[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int v = (warp * BPT + sp + u) * 32 + lane;
+            d[u] = sStage[warp][(sp + u) * 32 + lane];            // written by this lane
+            flag[u] = sFlag[v];
+            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20;
+            // window words (blocks without bases read the front padding)
+            ta[u] = __ldg(P.t.planes + d[u].tW); tb[u] = __ldg(P.t.planes + d[u].tW + 1);
+            qa[u] = __ldg(P.q.planes + d[u].qW); qb[u] = __ldg(P.q.planes + d[u].qW + 1);
+            // N summaries of both windows: one word each unless the window crosses an 8 kb line
+            const uint32_t span = n ? n - 1 : 0u;
+            const uint32_t tw0 = d[u].tW >> 3, tw1 = (d[u].tW + (((misc & 31u) + span) >> 5)) >> 3;
+            const uint32_t qw0 = d[u].qW >> 3, qw1 = (d[u].qW + ((((misc >> 5) & 31u) + span) >> 5)) >> 3;
+            tN[u] = __ldg(P.t.nwin + (tw0 >> 5)) & (0xffffffffu << (tw0 & 31)) & (0xffffffffu >> (31 - (tw1 & 31)));
+            qN[u] = __ldg(P.q.nwin + (qw0 >> 5)) & (0xffffffffu << (qw0 & 31)) & (0xffffffffu >> (31 - (qw1 & 31)));
+            slow[u] = (tw0 >> 5) != (tw1 >> 5) || (qw0 >> 5) != (qw1 >> 5);
+            // gap cost: shared table below smallSize, dense table in L2 up to the last knot
+            const uint32_t gv = d[u].excl;
+            gDense[u] = 0;
+            if (gv >= (uint32_t)P.gap.smallSize && gv < (uint32_t)P.gap.denseSize)
+                gDense[u] = __ldg(P.gapDense + (size_t)((flag[u] >> 4) & 3u) * P.gap.denseSize + gv);
+        }
+        int score[2], gap[2];
+        bool mayN[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20, tSh = misc, qSh = misc >> 5;
+            const uint32_t gv = d[u].excl, which = (flag[u] >> 4) & 3u;
+            const uint32_t sIdx = gv < (uint32_t)P.gap.smallSize ? gv : 0u;
+            const int gSm = gSmall[which * P.gap.smallSize + sIdx];
+            gap[u] = gv < (uint32_t)P.gap.smallSize ? gSm : gDense[u];
+            const uint32_t t1 = __funnelshift_r(ta[u].x, tb[u].x, tSh), t0 = __funnelshift_r(ta[u].y, tb[u].y, tSh);
+            const uint32_t q1 = __funnelshift_r(qa[u].x, qb[u].x, qSh), q0 = __funnelshift_r(qa[u].y, qb[u].y, qSh);
+            const int nv = n >= 32 ? 32 : (int)n;
+            score[u] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, shrOnes(32u - (uint32_t)nv), nv);
+            mayN[u] = n && (slow[u] || (tN[u] | qN[u]) != 0);
+        }
+        // rare: N inside a window, a window longer than the summary word, a gap beyond the dense table
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20, tSh = misc, qSh = misc >> 5;
+            if (mayN[u]) {
+                if (slow[u]) mayN[u] = wordsTouchN(P.t.nwin, d[u].tW, d[u].tW + (((tSh & 31u) + n - 1) >> 5)) ||
+                                       wordsTouchN(P.q.nwin, d[u].qW, d[u].qW + (((qSh & 31u) + n - 1) >> 5));
+                if (mayN[u]) {
+                    const uint32_t t1 = __funnelshift_r(ta[u].x, tb[u].x, tSh), t0 = __funnelshift_r(ta[u].y, tb[u].y, tSh);
+                    const uint32_t q1 = __funnelshift_r(qa[u].x, qb[u].x, qSh), q0 = __funnelshift_r(qa[u].y, qb[u].y, qSh);
+                    const uint32_t vmask = shrOnes(n >= 32 ? 0u : 32u - n) & nFreeMask(P.t.nplane, d[u].tW, tSh, P.q.nplane, d[u].qW, qSh);
+                    score[u] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, __popc(vmask));
                 }
             }
+            if ((int)d[u].excl < 0 || d[u].excl >= (uint32_t)P.gap.denseSize)
+                gap[u] = gapCostOf(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, (flag[u] >> 4) & 3u, d[u].excl);
         }
-        // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
-        // last block, or fetches it when this is the warp's first sub-tile
-        const int te = ts + len, qe = qs + len;
-        int pte = __shfl_up_sync(FULL, te, 1), pqe = __shfl_up_sync(FULL, qe, 1);
-        if (lane == 0) {
-            pte = carryTe; pqe = carryQe;
-            if (sub == 0 && valid && !(flag & 1) && bi > 0 && (unsigned long long)bi < P.nBlocks) {
-                int pts, pqs, plen; bool pj;
-                clipBlock(loadBlock(P.blocks, bi - 1), job.clipStart, job.clipEnd, pts, pqs, plen, pj);
-                pte = pts + plen; pqe = pqs + plen;
+        __syncwarp();
+        // what is left of a block joins the warp's item list, compacted in place: a slot index never
+        // exceeds the position its block had, and every lane has read its descriptor by now
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int v = (warp * BPT + sp + u) * 32 + lane;
+            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20;
+            sScore[v] = score[u];
+            sGap[v] = gap[u];
+            anyN |= mayN[u];
+            const bool listed = n > 32;
+            const uint32_t lb = __ballot_sync(FULL, listed);
+            if (listed) {
+                const int slot = nSlots + __popc(lb & (leMask >> 1));
+                sStage[warp][slot] = StageRec{d[u].tW + 1, d[u].qW + 1, (n - 32) | ((misc | (mayN[u] ? 0x800u : 0u)) << 20), (n - 1) >> 5};   // excl = item count for now
+                sSlotV[warp * TILE + slot] = (unsigned char)((sp + u) * 32 + lane);
             }
+            nSlots += __popc(lb);
         }
-        carryTe = __shfl_sync(FULL, te, 31); carryQe = __shfl_sync(FULL, qe, 31);
-        int gap = 0;
-        if (valid && !(flag & 1)) {
-            if (joined) flag |= 4;
-            else gap = gapCost(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, qs - pqe, ts - pte);
+    }
+#else
+    // pass B
+#pragma unroll P1_UNROLL
+    for (int sub = 0; sub < BPT; sub++) {
+        const int v = (warp * BPT + sub) * 32 + lane;
+        const StageRec d = sStage[warp][sub * 32 + lane];      // written by this lane
+        const uint32_t n = d.nMisc & 0xfffffu, misc = d.nMisc >> 20, tSh = misc, qSh = misc >> 5;
+        const uint32_t flag = sFlag[v];
+        // window words (blocks without bases read the front padding) and the N summaries of both windows
+        const uint2 ta = __ldg(P.t.planes + d.tW), tb = __ldg(P.t.planes + d.tW + 1);
+        const uint2 qa = __ldg(P.q.planes + d.qW), qb = __ldg(P.q.planes + d.qW + 1);
+        bool mayN = false;
+        if (n) mayN = wordsTouchN(P.t.nwin, d.tW, d.tW + (((tSh & 31u) + n - 1) >> 5)) ||
+                      wordsTouchN(P.q.nwin, d.qW, d.qW + (((qSh & 31u) + n - 1) >> 5));
+        sGap[v] = gapCostOf(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, (flag >> 4) & 3u, d.excl);
+        const uint32_t t1 = __funnelshift_r(ta.x, tb.x, tSh), t0 = __funnelshift_r(ta.y, tb.y, tSh);
+        const uint32_t q1 = __funnelshift_r(qa.x, qb.x, qSh), q0 = __funnelshift_r(qa.y, qb.y, qSh);
+        int nv = n >= 32 ? 32 : (int)n;
+        uint32_t vmask = shrOnes(32u - (uint32_t)nv);
+        if (mayN) {
+            vmask &= nFreeMask(P.t.nplane, d.tW, tSh, P.q.nplane, d.qW, qSh);
+            nv = __popc(vmask);
         }
-        sGap[v] = gap;
-        sFlag[v] = flag;
-        // the block's first 32 bases are scored right here (lane = block, no item bookkeeping);
-        // only what is left joins the warp's item list
-        const bool minus = (misc >> 10) & 1u;
-        int s0 = 0;
-        if (n) {
-            const uint32_t tSh = misc, qSh = misc >> 5;          // funnel shifts use the low 5 bits
-            uint32_t t1, t0, q1, q0;
-            loadWindow(P.t.planes, tW, tSh, t1, t0);
-            loadWindow(P.q.planes, qW, qSh, q1, q0);
-            const uint32_t r1 = ~__brev(q1), r0 = __brev(q0);     // reverse, complement = flip bit1
-            q1 = minus ? r1 : q1; q0 = minus ? r0 : q0;
-            uint32_t vmask = shrOnes(n >= 32 ? 0u : 32u - n);
-            int nv = n >= 32 ? 32 : (int)n;
-            if ((misc >> 11) & 1u) {
-                uint32_t nt = loadNWindow(P.t.nplane, tW, tSh);
-                uint32_t nq = loadNWindow(P.q.nplane, qW, qSh);
-                if (minus) nq = __brev(nq);
-                vmask &= ~(nt | nq);            // N scores 0 against everything (axt.c:431-454)
-                nv = __popc(vmask);
-            }
-            s0 = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
-        }
-        sScore[v] = s0;
+        sScore[v] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
+        anyN |= mayN;
+        // what is left of the block joins the warp's item list, compacted in place: a slot index never
+        // exceeds the position its block had, and every lane has read its descriptor by now
         const bool listed = n > 32;
         const uint32_t lb = __ballot_sync(FULL, listed);
+        __syncwarp();
         if (listed) {
-            const int slot = nSlots + __popc(lb & ((1u << lane) - 1u));
-            sStage[warp][slot] = StageRec{tW + 1, minus ? qW - 1 : qW + 1, (n - 32) | (misc << 20), (n - 1) >> 5};   // excl = item count for now
+            const int slot = nSlots + __popc(lb & (leMask >> 1));
+            sStage[warp][slot] = StageRec{d.tW + 1, d.qW + 1, (n - 32) | ((misc | (mayN ? 0x800u : 0u)) << 20), (n - 1) >> 5};   // excl = item count for now
             sSlotV[warp * TILE + slot] = (unsigned char)(sub * 32 + lane);
         }
         nSlots += __popc(lb);
     }
+#endif
     anyN = __any_sync(FULL, anyN);
+    GAT_TICK(1)
 
     // ---- phase 2: what is left of the warp's blocks as one list of 32-base items, dealt to lanes round
     // by round (adjacent lanes = adjacent items: coalesced).  Lane l speaks for list slots 4l..4l+3 when the
@@ -664,7 +824,6 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             st[0].excl = ex0; st[1].excl = ex1; st[2].excl = ex2; st[3].excl = ex3;
         }
         uint32_t *bits = sBits[warp];
-        const uint32_t leMask = 0xffffffffu >> (31 - lane);
         const uint2 *__restrict__ tPlanes = P.t.planes, *__restrict__ qPlanes = P.q.planes;
         int before = 0;                         // list slots that start before the round being fetched
         int sRun = 0;                           // sum of all item scores of earlier rounds (mod 2^32)
@@ -695,26 +854,20 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
                 MISC = rec.nMisc >> 20;                                                                     \
                 LEFT = (int)(rec.nMisc & 0xfffffu) - (int)(k << 5);                                         \
                 const uint2 *tp = tPlanes + (rec.tW + k);                                                   \
-                const uint2 *qp = qPlanes + ((MISC & 0x400u) ? rec.qW - k : rec.qW + k);                    \
+                const uint2 *qp = qPlanes + (rec.qW + k);                                                   \
                 W0 = __ldg(tp); W1 = __ldg(tp + 1); W2 = __ldg(qp); W3 = __ldg(qp + 1);                     \
             }
 #define GAT_CONSUME(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                      \
             {                                                                                               \
                 const uint32_t tSh = MISC, qSh = MISC >> 5;                                                 \
                 const uint32_t t1 = __funnelshift_r(W0.x, W1.x, tSh), t0 = __funnelshift_r(W0.y, W1.y, tSh);\
-                uint32_t q1 = __funnelshift_r(W2.x, W3.x, qSh), q0 = __funnelshift_r(W2.y, W3.y, qSh);      \
-                const uint32_t r1 = ~__brev(q1), r0 = __brev(q0);                                           \
-                const bool minus = (MISC & 0x400u) != 0;                                                    \
-                q1 = minus ? r1 : q1; q0 = minus ? r0 : q0;                                                 \
+                const uint32_t q1 = __funnelshift_r(W2.x, W3.x, qSh), q0 = __funnelshift_r(W2.y, W3.y, qSh);\
                 int nv = LEFT > 32 ? 32 : (LEFT < 0 ? 0 : LEFT);                                            \
                 uint32_t vmask = shrOnes(32u - (uint32_t)nv);                                               \
                 if (anyN && (MISC & 0x800u) && nv) {                                                        \
                     const StageRec rec = sStage[warp][OW];                                                  \
                     const uint32_t k = idx0 + ((uint32_t)(R) << 5) - rec.excl;                              \
-                    uint32_t nt = loadNWindow(P.t.nplane, rec.tW + k, tSh);                                 \
-                    uint32_t nq = loadNWindow(P.q.nplane, minus ? rec.qW - k : rec.qW + k, qSh);            \
-                    if (minus) nq = __brev(nq);                                                             \
-                    vmask &= ~(nt | nq);                                                                    \
+                    vmask &= nFreeMask(P.t.nplane, rec.tW + k, tSh, P.q.nplane, rec.qW + k, qSh);           \
                     nv = __popc(vmask);                                                                     \
                 }                                                                                           \
                 int x = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);                                \
@@ -748,6 +901,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         }
     }
     __syncwarp();
+    GAT_TICK(2)
 
     // ---- phase 3: ordered segmented reduction of tuples, per warp: lane l walks job-blocks 4l..4l+3
     // of the warp, one warp scan joins the lanes; what crosses warps is resolved by whichever warp
@@ -767,9 +921,10 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         const uint32_t myWr = __shfl_sync(FULL, wrank, wsel), myHw = sHead[wsel];
         if (small) warpJobReduce<int>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
                                       sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
-        else warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
-                                      sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
+        else warpJobReduceWide(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
+                               sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
     }
+    GAT_TICK(3)
     // last warp of the CTA to get here stitches the warps together
     __threadfence_block();
     __syncwarp();
@@ -812,16 +967,14 @@ __global__ void fixupKernel(const JobInfo *__restrict__ info, unsigned long long
     const unsigned long long np = info[j + 1].blockPtr;
     const uint32_t cLast = (uint32_t)((np - 1) / CHUNK);
     const uint32_t count = cLast - c;                  // heads to fold: chunks c+1 .. cLast
-    const uint32_t per = (count + 31) / 32;
-    Tup mine = tupIdentity();
-    for (uint32_t i = 0; i < per; i++) {
-        uint32_t idx = lane * per + i;
-        if (idx < count) mine = tupCombine(mine, chunkHead[c + 1 + idx]);
-    }
     Tup all = chunkTail[c];
-    for (int l = 0; l < 32; l++) {
-        Tup o = tupShfl(mine, l);
-        all = tupCombine(all, o);
+    for (uint32_t base = 0; base < count; base += 32) {           // 32 consecutive heads per step, folded in order
+        Tup x = base + lane < count ? chunkHead[c + 1 + base + lane] : tupIdentity();
+        for (int off = 1; off < 32; off <<= 1) {
+            const Tup o = tupShfl(x, lane + off < 32 ? lane + off : lane);
+            if (lane + off < 32) x = tupCombine(x, o);
+        }
+        all = tupCombine(all, x);                                 // lane 0 holds the fold
     }
     if (lane == 0) {
         outGlobal[j] = all.d;
@@ -883,6 +1036,40 @@ __global__ void nRunKernel(const gat_nrun *__restrict__ runs, unsigned long long
     }
     for (unsigned long long win = (g0 >> NWIN_SHIFT) + lane; win <= ((g1 - 1) >> NWIN_SHIFT); win += 32)
         atomicOr(&nwin[win >> 5], 1u << (win & 31));
+}
+
+// Reverse-complement copy of the query (the reference keeps one per '-' chromosome, scoreChain.c:123-149):
+// sequence s of size n gets a second image at seqBase[nSeq + s] whose base p is the complement of forward
+// base n-1-p, so '-' chains read forward in their own coordinates.  One thread per 32-base word of a copy.
+__global__ void revCompKernel(const uint32_t *__restrict__ seqSize, const long long *__restrict__ seqBase,
+                              const unsigned long long *__restrict__ seqWordStart, uint32_t nSeq,
+                              unsigned long long totalWords, uint2 *__restrict__ planes, uint32_t *__restrict__ nplane,
+                              uint32_t *__restrict__ nwin)
+{
+    unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= totalWords) return;
+    uint32_t lo = 0, hi = nSeq;          // last sequence with seqWordStart <= w
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (seqWordStart[mid] <= w) lo = mid; else hi = mid;
+    }
+    const uint32_t s = lo;
+    const long long wl = (long long)(w - seqWordStart[s]);
+    const long long size = seqSize[s];
+    // rc bases [32wl, 32wl+32) are forward bases (e-32 .. e-1] read downwards, e = size - 32wl
+    const long long e = size - 32 * wl;                       // > 0
+    const long long fBase = seqBase[s] + e - 32;              // forward padded coordinate of the window start (may precede the sequence)
+    const long long fw = fBase >> 5;                          // floor: seqBase >= 1152
+    const uint32_t sh = (uint32_t)(fBase & 31);
+    const uint2 a = planes[fw], b = planes[fw + 1];
+    const uint32_t hiW = __funnelshift_r(a.x, b.x, sh), loW = __funnelshift_r(a.y, b.y, sh);
+    const uint32_t nW = __funnelshift_r(nplane[fw], nplane[fw + 1], sh);
+    const uint32_t keep = e >= 32 ? 0xffffffffu : (0xffffffffu >> (32 - (int)e));   // rc positions that exist
+    const unsigned long long n = (unsigned long long)(seqBase[nSeq + s] >> 5) + (unsigned long long)wl;
+    planes[n] = make_uint2(~__brev(hiW) & keep, __brev(loW) & keep);
+    const uint32_t rn = __brev(nW) & keep;
+    nplane[n] = rn;
+    if (rn) atomicOr(&nwin[(n >> 3) >> 5], 1u << ((n >> 3) & 31));
 }
 
 }  // namespace gat

@@ -18,7 +18,28 @@ for w in want:
         print('%-66s %-10s %s' % (w, rows[1][i], rows[2][i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--print-kernel-base", "function"],
                      capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
+def split_row(line, ncols=None):
+    # ncu does not escape quotes inside the source column: split it off by position
+    line = line.rstrip('\n')
+    if not line.startswith('"'):
+        return next(csv.reader([line]), [])
+    body = line[1:-1] if line.endswith('"') else line[1:]
+    if ncols is None:
+        return body.split('","')
+    first, rest = body.split('","', 1)
+    tail = rest.rsplit('","', ncols - 2)
+    return [first] + tail
+raw_lines = src.split('\n')
+hdr_cols = None
+rows = []
+for ln in raw_lines:
+    if ln.startswith('"Line No"'):
+        hdr_cols = len(split_row(ln))
+        rows.append(split_row(ln))
+    elif hdr_cols and ln.startswith('"'):
+        rows.append(split_row(ln, hdr_cols))
+    else:
+        rows.append(next(csv.reader([ln]), []) if ln else [])
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Line No']
 h = rows[hi[0]]
 ci, si = h.index('Instructions Executed'), h.index('# Samples')
