@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mean-log-len", type=float, default=3.6, help="block length ~ lognormal(mu, 1.1); 3.6 = the benchmark (mean 67 bp)")
     ap.add_argument("--max-len", type=int, default=30000)
+    ap.add_argument("--fold", type=int, default=0, help="experiment: fold block coordinates into the first FOLD bases of their sequences (cache-resident genome)")
     ap.add_argument("--split", type=int, default=0, help="cut blocks longer than this into JOINED records (0 = as generated)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -301,6 +302,10 @@ def main():
         w.alg_blocks = w.total
         w.jobs, w.total, w.blocks = split_long_blocks(w.jobs, w.total, w.blocks, args.split)
         assert w.aligned_bp == bp
+    if args.fold:
+        small = w.blocks["size"] < 300
+        w.blocks["tStart"][small] %= args.fold
+        w.blocks["qStart"][small] %= args.fold
     # our kernels launch on this torch stream, so torch's CUDA events bracket them
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)

@@ -71,6 +71,8 @@ struct gat_worklist {
     uint64_t nJobs = 0, totalJobBlocks = 0, nBlocks = 0;
     uint32_t nChunks = 0;
     uint32_t *chunkJob = nullptr;
+    uint32_t *headBits = nullptr;       // job-start bitmap over job-blocks (jobPrepKernel), CHUNK/32 words per chunk + slack
+    bool borrowedBlocks = false;        // blocks belong to another work-list (re-run without empty jobs)
     Tup *chunkHead = nullptr, *chunkTail = nullptr;
     int *chunkTailJob = nullptr;
     long long *outGlobal = nullptr, *outLocal = nullptr;
@@ -78,9 +80,9 @@ struct gat_worklist {
 
 static void freeWorklistBuffers(gat_worklist *wl)
 {
-    cudaFree(wl->jobs); cudaFree(wl->info); cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->chunkHead);
+    cudaFree(wl->jobs); cudaFree(wl->info); if (!wl->borrowedBlocks) cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->headBits); cudaFree(wl->chunkHead);
     cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal);
-    wl->jobs = nullptr; wl->info = nullptr; wl->blocks = nullptr; wl->chunkJob = nullptr; wl->chunkHead = wl->chunkTail = nullptr;
+    wl->jobs = nullptr; wl->info = nullptr; wl->blocks = nullptr; wl->chunkJob = nullptr; wl->headBits = nullptr; wl->chunkHead = wl->chunkTail = nullptr;
     wl->chunkTailJob = nullptr; wl->outGlobal = wl->outLocal = nullptr;
     wl->capJobs = wl->capBlocks = wl->capChunks = 0;
 }
@@ -335,9 +337,7 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->dynSmem = (size_t)3 * L * sizeof(double) + (size_t)L * sizeof(int) + (size_t)3 * S * sizeof(int);
-    CU(cudaFuncSetAttribute(scoreChunksKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->dynSmem));
-    CU(cudaFuncSetAttribute(scoreChunksKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->dynSmem));
+    ctx->dynSmem = 0;       // the small gap tables are read through L1
     {
         int perSm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, scoreChunksKernel<true>, TPB, ctx->dynSmem));
@@ -364,8 +364,9 @@ static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_
         freeWorklistBuffers(wl);
         CU(cudaMalloc(&wl->jobs, (cj + 1) * sizeof(gat_job)));
         CU(cudaMalloc(&wl->info, (cj + 1) * sizeof(JobInfo)));
-        CU(cudaMalloc(&wl->blocks, (cb + 1) * sizeof(gat_block)));
+        if (!wl->borrowedBlocks) CU(cudaMalloc(&wl->blocks, (cb + 1) * sizeof(gat_block)));
         CU(cudaMalloc(&wl->chunkJob, (cc + 1) * sizeof(uint32_t)));
+        CU(cudaMalloc(&wl->headBits, (cc + 2) * (CHUNK / 32) * sizeof(uint32_t)));
         CU(cudaMalloc(&wl->chunkHead, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTail, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTailJob, (cc + 1) * sizeof(int)));
@@ -434,7 +435,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     ScoreParams P;
     P.info = wl->info; P.blocks = wl->blocks;
     P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
-    P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks;
+    P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks; P.headBits = wl->headBits;
     P.maxBlockBases = ctx->maxBlockBases;
     P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
     memcpy(P.coef, ctx->coef, sizeof P.coef);
@@ -446,12 +447,13 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
 
     const bool prof = ctx->profiling;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaMemsetAsync(wl->headBits, 0, ((size_t)wl->nChunks + 2) * (CHUNK / 32) * sizeof(uint32_t), st));
     {
         const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
         unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
         jobPrepKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
                                             (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
-                                            wl->outGlobal, wl->outLocal, ctx->err);
+                                            wl->headBits, wl->outGlobal, wl->outLocal, ctx->err);
     }
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
     if (ctx->sym) scoreChunksKernel<true><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
@@ -478,20 +480,61 @@ static int finishStats(gat_ctx *ctx)
     return GAT_OK;
 }
 
-static int checkDeviceError(gat_ctx *ctx)
+static int readDeviceError(gat_ctx *ctx, int *err)
 {
-    int err = 0;
-    CU(cudaMemcpyAsync(&err, ctx->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    *err = 0;
+    CU(cudaMemcpyAsync(err, ctx->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (err) {
-        cudaMemsetAsync(ctx->err, 0, sizeof(int), ctx->stream);
-        return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s%s%s",
-                    (err & ERR_SEQ) ? " sequence index out of range;" : "",
-                    (err & ERR_BLOCKIDX) ? " block index out of range;" : "",
-                    (err & ERR_COORD) ? " block coordinates outside their sequence;" : "",
-                    (err & ERR_TOOLONG) ? " a record longer than gat_max_record_bases() (split it with GAT_BLOCK_JOINED);" : "",
-                    (err & ERR_CSR) ? " blockPtr is not a non-decreasing CSR row pointer starting at 0;" : "");
+    if (*err) CU(cudaMemsetAsync(ctx->err, 0, sizeof(int), ctx->stream));
+    return GAT_OK;
+}
+
+static int rejectWorklist(int err)
+{
+    return fail(GAT_EWORKLIST, "work-list rejected by the device:%s%s%s%s%s",
+                (err & ERR_SEQ) ? " sequence index out of range;" : "",
+                (err & ERR_BLOCKIDX) ? " block index out of range;" : "",
+                (err & ERR_COORD) ? " block coordinates outside their sequence;" : "",
+                (err & ERR_TOOLONG) ? " a record longer than gat_max_record_bases() (split it with GAT_BLOCK_JOINED);" : "",
+                (err & ERR_CSR) ? " blockPtr is not a non-decreasing CSR row pointer starting at 0;" : "");
+}
+
+// The scoring kernel numbers jobs by counting job starts, which presumes that every job owns at least one
+// job-block.  Work-lists with empty jobs (a sub-chain that clips to nothing: kent's NULL sub-chain, score 0)
+// are rare; jobPrepKernel flags them and the list is scored again here without them.
+static int rerunWithoutEmptyJobs(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local)
+{
+    std::vector<gat_job> all(wl->nJobs), kept;
+    std::vector<uint64_t> origin;
+    CU(cudaMemcpyAsync(all.data(), wl->jobs, wl->nJobs * sizeof(gat_job), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t j = 0; j < wl->nJobs; j++) {
+        const uint64_t np = j + 1 < wl->nJobs ? all[j + 1].blockPtr : wl->totalJobBlocks;
+        if (np > all[j].blockPtr) { kept.push_back(all[j]); origin.push_back(j); }
     }
+    gat_worklist tmp;
+    tmp.borrowedBlocks = true;
+    int rc = shapeWorklist(ctx, &tmp, kept.size(), wl->totalJobBlocks, wl->nBlocks);
+    tmp.blocks = wl->blocks;
+    std::vector<int64_t> g(kept.size()), l(kept.size());
+    if (rc == GAT_OK && !kept.empty()) {
+        cudaError_t e = cudaMemcpyAsync(tmp.jobs, kept.data(), kept.size() * sizeof(gat_job), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail(GAT_ECUDA, "work-list upload failed: %s", cudaGetErrorString(e));
+        if (rc == GAT_OK) rc = gat_worklist_run(ctx, &tmp);
+        if (rc == GAT_OK) {
+            cudaMemcpyAsync(g.data(), tmp.outGlobal, g.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(l.data(), tmp.outLocal, l.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            int err = 0;
+            rc = readDeviceError(ctx, &err);
+            if (rc == GAT_OK && err) rc = rejectWorklist(err);
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    tmp.blocks = nullptr;
+    freeWorklistBuffers(&tmp);
+    if (rc != GAT_OK) return rc;
+    for (uint64_t j = 0; j < wl->nJobs; j++) { if (global) global[j] = 0; if (local) local[j] = 0; }
+    for (size_t k = 0; k < kept.size(); k++) { if (global) global[origin[k]] = g[k]; if (local) local[origin[k]] = l[k]; }
     return GAT_OK;
 }
 
@@ -503,8 +546,14 @@ extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *glo
         if (global) CU(cudaMemcpyAsync(global, wl->outGlobal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         if (local) CU(cudaMemcpyAsync(local, wl->outLocal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    int rc = checkDeviceError(ctx);
+    int err = 0;
+    int rc = readDeviceError(ctx, &err);
     if (rc != GAT_OK) return rc;
+    if (err & ~ERR_EMPTYJOB) return rejectWorklist(err);
+    if (err & ERR_EMPTYJOB) {
+        rc = rerunWithoutEmptyJobs(ctx, wl, global, local);
+        if (rc != GAT_OK) return rc;
+    }
     return finishStats(ctx);
 }
 

@@ -37,6 +37,7 @@ constexpr int PAD_BACK_GROUPS = 10;
 constexpr int NWIN_SHIFT = 8;          // N summary: one bit per 256 bases
 
 constexpr int ERR_SEQ = 1, ERR_BLOCKIDX = 2, ERR_COORD = 4, ERR_TOOLONG = 8, ERR_CSR = 16;
+constexpr int ERR_EMPTYJOB = 32;   // not an error: a job without blocks; the host re-runs the list without such jobs
 
 struct GenomeView {
     const uint2 *planes;      // word n = {high bits, low bits} of bases [32n, 32n+32)
@@ -124,6 +125,7 @@ struct ScoreParams {
     const gat_block *blocks;
     unsigned long long nJobs, totalJobBlocks, nBlocks;
     const uint32_t *chunkJob;   // job containing the first job-block of each chunk
+    const uint32_t *headBits;   // bit b: a (non-empty) job starts at job-block b; bit totalJobBlocks closes the list
     uint32_t nChunks;
     uint32_t maxBlockBases;     // records longer than this are rejected (32-bit block sums)
     GenomeView t, q;
@@ -316,6 +318,7 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
                               const int64_t *__restrict__ tSeqBase, const uint32_t *__restrict__ tSeqSize, uint32_t tNSeq,
                               const int64_t *__restrict__ qSeqBase, const uint32_t *__restrict__ qSeqSize, uint32_t qNSeq,
                               JobInfo *__restrict__ info, uint32_t *__restrict__ chunkJob, uint32_t nChunks,
+                              uint32_t *__restrict__ headBits,
                               long long *__restrict__ outGlobal, long long *__restrict__ outLocal, int *__restrict__ err)
 {
     const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,9 +345,10 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
             o.tSize = __ldg(tSeqSize + job.tSeq);
             o.qSize = __ldg(qSeqSize + qSeq);
         }
+        if (np <= bp) { outGlobal[j] = 0; outLocal[j] = 0; e |= ERR_EMPTYJOB; }
         if (e) atomicOr(err, e);
-        if (np <= bp) { outGlobal[j] = 0; outLocal[j] = 0; }
-        else if (!(e & ERR_CSR)) {
+        if (np > bp && !(e & ERR_CSR)) {
+            atomicOr(&headBits[bp >> 5], 1u << (bp & 31));
             c0 = (bp + CHUNK - 1) / CHUNK;
             c1 = (np + CHUNK - 1) / CHUNK;
             if (c1 > nChunks) c1 = nChunks;
@@ -361,6 +365,7 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
         for (unsigned long long c = b0 + lane; c < b1; c += 32) chunkJob[c] = jj;
     }
     if (j > nJobs) return;
+    if (j == nJobs) atomicOr(&headBits[total >> 5], 1u << (total & 31));
     uint4 *dst = reinterpret_cast<uint4 *>(info + j);
     dst[0] = make_uint4(o.tBaseW, o.qBaseW, o.tSize, o.qSize);
     dst[1] = make_uint4((uint32_t)o.clipStart, (uint32_t)o.clipEnd, o.delta, o.blockPtr);
@@ -371,13 +376,10 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
 struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 
 #ifndef GAT_MIN_CTAS
-#define GAT_MIN_CTAS 5
+#define GAT_MIN_CTAS 4
 #endif
 #ifndef GAT_P1_UNROLL
 #define GAT_P1_UNROLL 1
-#endif
-#ifndef GAT_PASSB_PAIR
-#define GAT_PASSB_PAIR 0
 #endif
 #ifndef GAT_PREFETCH
 #define GAT_PREFETCH 1      // bit 0: first genome sectors of each block, from phase 1
@@ -418,7 +420,7 @@ __device__ __forceinline__ long long finalLocal(const Tup &t) { return max64(0, 
 // 4l..4l+3 of the warp: scores a[], gap costs g[] (the gap BEFORE the block), flags fl4 (one byte each).
 template <typename T>
 __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
-                                              uint32_t myWr, uint32_t myHw, const uint32_t *sJobSlot, int warpV0, int vEnd,
+                                              uint32_t myWr, uint32_t myHw, int warpV0, int vEnd,
                                               int warp, int lane, Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead,
                                               int *sWarpPendJob, int *sLastIsEnd, uint32_t *sLastJob)
 {
@@ -446,16 +448,14 @@ __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&
             }
             const int v = warpV0 + BPT * lane + k;
             if (fl & 2) {
-                const uint32_t rank = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31)))) - 1;
-                const uint32_t job = sJobSlot[rank];
+                const uint32_t job = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31))));
                 if (runHasHead) {   // job lies inside my run: done
                     P.outGlobal[job] = (long long)cur.d;
                     P.outLocal[job] = finalLocal(cur);
                 } else { pend = true; pendTup = cur; pendJob = job; }
                 if (v + 1 == vEnd) { *sLastIsEnd = 1; *sLastJob = job; }
             } else if (v + 1 == vEnd) {          // the chunk's last valid job-block: its job runs on
-                const uint32_t rank = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31)))) - 1;
-                *sLastIsEnd = 0; *sLastJob = sJobSlot[rank];
+                *sLastIsEnd = 0; *sLastJob = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31))));
             }
         }
     }
@@ -495,11 +495,11 @@ __device__ unsigned long long gTiming[8];   // sum over warps of clocks spent pe
 
 // the 64-bit form is rare (a warp whose 128 blocks sum past 2^27): keep it out of the hot instruction stream
 __device__ __noinline__ void warpJobReduceWide(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
-                                               uint32_t myWr, uint32_t myHw, const uint32_t *sJobSlot, int warpV0, int vEnd,
+                                               uint32_t myWr, uint32_t myHw, int warpV0, int vEnd,
                                                int warp, int lane, Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead,
                                                int *sWarpPendJob, int *sLastIsEnd, uint32_t *sLastJob)
 {
-    warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane, sWarpAgg, sWarpPend, sWarpHead,
+    warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane, sWarpAgg, sWarpPend, sWarpHead,
                              sWarpPendJob, sLastIsEnd, sLastJob);
 }
 
@@ -510,78 +510,43 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
 #ifdef GAT_TIMING
     long long tick_ = clock64();
 #endif
-    __shared__ uint32_t sHead[CHUNK / 32 + 1];  // bit v: a job starts at job-block v of the chunk (bit 0: always; bit vEnd: end of list)
-    __shared__ uint32_t sJobSlot[CHUNK + 1];    // job index of the r-th head
     __shared__ __align__(16) int sGap[CHUNK];   // cost of the gap in front of the block
     __shared__ __align__(16) int sScore[CHUNK]; // block score: first 32 bases from phase 1, the rest added after phase 2
     __shared__ __align__(16) int sEnd[CHUNK];   // per list slot: running item-score sum of the warp at the slot's last item (mod 2^32)
-    __shared__ unsigned char sSlotV[CHUNK];     // per list slot: its block (index inside the warp's tile)
-    __shared__ __align__(4) unsigned char sFlag[CHUNK];   // 1 head of job, 2 end of job, 4 continues the previous record, 8 valid
-    __shared__ StageRec sStage[WARPS][TILE];    // per warp: its blocks expanded to items
+    __shared__ __align__(16) uint32_t sEx[CHUNK];   // per list slot: its item count, then the items of the warp's list in front of it
+    __shared__ __align__(4) unsigned char sSlotV[CHUNK];   // per list slot: its block (index inside the warp's tile)
+    __shared__ __align__(4) unsigned char sFlag[CHUNK];   // 1 head of job, 2 end of job, 4 continues the previous record, 8 valid, 16|32 gap table
+    __shared__ StageRec sStage[WARPS][TILE];    // per warp: its blocks' windows, then its item list
     __shared__ uint32_t sBits[WARPS][32];       // scratch for the item-head bitmap of a pass
     __shared__ Tup sWarpAgg[WARPS], sWarpPend[WARPS];
     __shared__ int sWarpHead[WARPS], sWarpPendJob[WARPS];
-    __shared__ int sArrived, sLastIsEnd, sFirstIsHead;
+    __shared__ int sArrived, sLastIsEnd;
     __shared__ uint32_t sLastJob;
-    extern __shared__ unsigned char sDyn[];     // gap tables
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (*reinterpret_cast<volatile const int *>(P.err)) return;     // jobPrepKernel rejected the work-list
+    if (tid == 0) sArrived = 0;
+    __syncthreads();                    // the only CTA-wide barrier: from here on warps run on their own
+    // ---- phase 0 (per warp, three independent loads): the chunk's 32 words of the job-start bitmap
+    // (jobPrepKernel), the job that owns the chunk's first block, the rejection flag.
     const uint32_t vb0 = blockIdx.x * (uint32_t)CHUNK;               // totalJobBlocks < 2^32
     const uint32_t total = (uint32_t)P.totalJobBlocks;
     const int vEnd = (int)(total - vb0 < (uint32_t)CHUNK ? total - vb0 : (uint32_t)CHUNK);   // valid job-blocks of this chunk
-    if (tid == 0) sArrived = 0;
-    for (int i = tid; i < CHUNK / 32 + 1; i += TPB) sHead[i] = 0;
-
-    // ---- stage gap tables (gapCalc.c:12-37) in shared memory
-    double *gLongVal = reinterpret_cast<double *>(sDyn);
-    int *gLongPos = reinterpret_cast<int *>(gLongVal + 3 * P.gap.longCount);
-    int *gSmall = gLongPos + P.gap.longCount;
-#pragma unroll 1
-    for (int i = tid; i < 3 * P.gap.longCount; i += TPB) gLongVal[i] = P.gapLongVal[i];
-#pragma unroll 1
-    for (int i = tid; i < P.gap.longCount; i += TPB) gLongPos[i] = P.gapLongPos[i];
-#pragma unroll 1
-    for (int i = tid; i < 3 * P.gap.smallSize; i += TPB) gSmall[i] = P.gapSmall[i];
-    __syncthreads();
-
-    // ---- phase 0: where jobs start inside this chunk (bitmap), and which job the r-th start is
+    const uint32_t myHeadWord = __ldg(P.headBits + (size_t)blockIdx.x * (CHUNK / 32) + lane);
+    const uint32_t nextHead0 = __ldg(P.headBits + (size_t)(blockIdx.x + 1) * (CHUNK / 32)) & 1u;
     const uint32_t j0 = __ldg(P.chunkJob + blockIdx.x);
-    const uint32_t jEnd = (blockIdx.x + 1 < P.nChunks) ? __ldg(P.chunkJob + blockIdx.x + 1) : (uint32_t)(P.nJobs - 1);
-    if (tid == 0) {
-        atomicOr(&sHead[0], 1u);                                       // the chunk's first block opens slot 0
-        if (vb0 + (uint32_t)vEnd == total) atomicOr(&sHead[vEnd >> 5], 1u << (vEnd & 31));   // nothing follows the last block
-        sFirstIsHead = __ldg(&P.info[j0].blockPtr) == vb0;
-    }
-    for (uint32_t j = j0 + tid; j <= jEnd; j += TPB) {
-        const uint32_t bp = __ldg(&P.info[j].blockPtr), np = __ldg(&P.info[j + 1].blockPtr);
-        if (np > bp && bp > vb0 && bp - vb0 <= (uint32_t)CHUNK) atomicOr(&sHead[(bp - vb0) >> 5], 1u << ((bp - vb0) & 31));
-    }
-    __syncthreads();
-    uint32_t wrank;                                                    // lane i: heads in words 0..i-1
+    if (*reinterpret_cast<volatile const int *>(P.err)) return;     // jobPrepKernel rejected the work-list (or met an empty job)
+    uint32_t wrank;     // lane i: jobs that start in words 0..i-1 of the chunk, not counting the chunk's first block
     {
-        const uint32_t pc = __popc(sHead[lane]);
+        const uint32_t pc = __popc(lane == 0 ? myHeadWord & ~1u : myHeadWord);
         uint32_t inc = pc;
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, inc, off);
             if (lane >= off) inc += o;
         }
-        wrank = inc - pc;
+        wrank = j0 + inc - pc;          // + j0: the job of block v is wrank(word) + starts in (word start, v], first block excluded
     }
-    for (uint32_t base = j0; base <= jEnd; base += TPB) {              // warp-uniform trip count (shuffle inside)
-        const uint32_t j = base + tid;
-        bool act = j <= jEnd;
-        uint32_t pos = 0;
-        if (act) {
-            const uint32_t bp = __ldg(&P.info[j].blockPtr), np = __ldg(&P.info[j + 1].blockPtr);
-            act = np > bp && (bp > vb0 ? bp - vb0 < (uint32_t)CHUNK : j == j0);
-            pos = bp > vb0 ? bp - vb0 : 0u;
-        }
-        const uint32_t wsel = (pos >> 5) & 31u;
-        const uint32_t wr = __shfl_sync(FULL, wrank, wsel);
-        if (act) sJobSlot[wr + __popc(sHead[wsel] & ((1u << (pos & 31)) - 1u))] = j;
-    }
-    __syncthreads();
+    const int *gSmall = P.gapSmall, *gLongPos = P.gapLongPos;       // L1-resident tables (gapCalc.c:12-37)
+    const double *gLongVal = P.gapLongVal;
 
     GAT_TICK(0)
     // ---- phase 1: this warp's TILE job-blocks, 32 at a time; block v = warp*TILE + sub*32 + lane.
@@ -592,44 +557,29 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     int nSlots = 0;                     // blocks of this warp with more than 32 bases: they get a slot in the item list
     const uint32_t leMask = 0xffffffffu >> (31 - lane);
     {
-        uint32_t jOf[BPT];
-        gat_block rec[BPT];
-        uint32_t okBits = 0;            // bit sub: my block of that sub-tile exists and its record index is in range
-        gat_block prevRec;              // lane 0: the record in front of the warp's first block
-        bool badIdx = false;
-#pragma unroll
+        int carryTe = 0, carryQe = 0;   // clipped ends of the previous sub-tile's last block
+        int errAcc = 0;
+#pragma unroll P1_UNROLL
         for (int sub = 0; sub < BPT; sub++) {
             const int wi = warp * BPT + sub;
             const int v = wi * 32 + lane;
-            const uint32_t hw = sHead[wi];
+            const uint32_t hw = __shfl_sync(FULL, myHeadWord, wi);
+            const uint32_t hwn = wi + 1 < 32 ? __shfl_sync(FULL, myHeadWord, (wi + 1) & 31) : nextHead0;
             const uint32_t wr = __shfl_sync(FULL, wrank, wi);
             const bool valid = v < vEnd;
-            const uint32_t rank = wr + __popc(hw & leMask) - 1;
-            jOf[sub] = valid ? sJobSlot[rank] : j0;
-            const uint32_t bi = vb0 + (uint32_t)v + __ldg(&P.info[jOf[sub]].delta);
+            const uint32_t jMine = valid ? wr + __popc(hw & (wi == 0 ? ~1u : ~0u) & leMask) : j0;
+            const JobInfo job = loadInfo(P.info, jMine);
+            const uint32_t bi = vb0 + (uint32_t)v + job.delta;
             const bool ok = valid && (unsigned long long)bi < P.nBlocks;
-            badIdx |= valid && !ok;
-            okBits |= ok ? 1u << sub : 0u;
-            rec[sub] = loadBlock(P.blocks, ok ? bi : 0u);
-            if (sub == 0) prevRec = loadBlock(P.blocks, ok && bi > 0 ? bi - 1 : 0u);
-        }
-        int carryTe = 0, carryQe = 0;   // clipped ends of the previous sub-tile's last block
-        int errAcc = badIdx ? ERR_BLOCKIDX : 0;
-        // straight-line code (selects, no branches) so that the four unrolled sub-tiles interleave
-#pragma unroll
-        for (int sub = 0; sub < BPT; sub++) {
-            const int wi = warp * BPT + sub;
-            const int v = wi * 32 + lane;
-            const uint32_t hw = sHead[wi], hwn = sHead[wi + 1];
-            const bool ok = (okBits >> sub) & 1u;
-            const JobInfo job = loadInfo(P.info, jOf[sub]);     // its line came in with delta
-            const bool isHead = v == 0 ? sFirstIsHead != 0 : ((hw >> lane) & 1u) != 0;
+            errAcc |= valid && !ok ? ERR_BLOCKIDX : 0;
+            const gat_block rec = loadBlock(P.blocks, ok ? bi : 0u);
+            const bool isHead = ((hw >> lane) & 1u) != 0;
             const bool isEnd = ((lane < 31 ? hw >> (lane + 1) : hwn) & 1u) != 0;
             uint32_t flag = v < vEnd ? (8u | (isHead ? 1u : 0u) | (isEnd ? 2u : 0u)) : 0u;
             // chainFastSubsetOnT clip (chain.c:513-522)
-            const bool joined = (rec[sub].size & GAT_BLOCK_JOINED) != 0;
-            int ts = rec[sub].tStart, qs = rec[sub].qStart;
-            int te = ts + (int)(rec[sub].size & 0x7fffffffu);
+            const bool joined = (rec.size & GAT_BLOCK_JOINED) != 0;
+            int ts = rec.tStart, qs = rec.qStart;
+            int te = ts + (int)(rec.size & 0x7fffffffu);
             const int cut = job.clipStart > ts ? job.clipStart - ts : 0;
             ts += cut; qs += cut;
             te = te > job.clipEnd ? job.clipEnd : te;
@@ -644,159 +594,55 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             const uint32_t n = ok && !bad && !tooLong ? (uint32_t)nn : 0u;
             const uint32_t tW = n ? job.tBaseW + ((uint32_t)ts >> 5) : 0u;
             const uint32_t qW = n ? job.qBaseW + ((uint32_t)qs >> 5) : 0u;
-            const uint32_t misc = ((uint32_t)ts & 31u) | (((uint32_t)qs & 31u) << 5);
-            // ask L2 for the first and the last sector of both windows (the same one for most blocks)
-            prefetchL2(P.t.planes + tW);
-            prefetchL2(P.q.planes + qW);
-            prefetchL2(P.t.planes + tW + ((((uint32_t)ts & 31u) + n) >> 5));
-            prefetchL2(P.q.planes + qW + ((((uint32_t)qs & 31u) + n) >> 5));
+            const uint32_t tSh = (uint32_t)ts & 31u, qSh = (uint32_t)qs & 31u;
+            // the block's first 32 bases are scored right here (lane = block, no item bookkeeping); blocks
+            // without bases read the front padding
+            const uint2 ta = __ldg(P.t.planes + tW), tb = __ldg(P.t.planes + tW + 1);
+            const uint2 qa = __ldg(P.q.planes + qW), qb = __ldg(P.q.planes + qW + 1);
+            bool mayN = false;
+            if (n) mayN = wordsTouchN(P.t.nwin, tW, tW + ((tSh + n - 1) >> 5)) || wordsTouchN(P.q.nwin, qW, qW + ((qSh + n - 1) >> 5));
             // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
             // last block, or the record fetched for that purpose when this is the warp's first sub-tile
             const int cte = ok ? te : 0, cqe = ok ? qs + len : 0;
             int pte = __shfl_up_sync(FULL, cte, 1), pqe = __shfl_up_sync(FULL, cqe, 1);
-            if (sub == 0) {
+            if (sub == 0 && lane == 0 && ok && !isHead && bi > 0) {     // the record in front of the warp's first block
                 int pts, pqs, plen; bool pj;
-                clipBlock(prevRec, job.clipStart, job.clipEnd, pts, pqs, plen, pj);
+                clipBlock(loadBlock(P.blocks, bi - 1), job.clipStart, job.clipEnd, pts, pqs, plen, pj);
                 carryTe = pts + plen; carryQe = pqs + plen;
             }
             pte = lane == 0 ? carryTe : pte; pqe = lane == 0 ? carryQe : pqe;
             carryTe = __shfl_sync(FULL, cte, 31); carryQe = __shfl_sync(FULL, cqe, 31);
-            // gap in front of the block, as (table, size): gapCalcCost's choice of table (gapCalc.c:304-330);
-            // the look-up itself waits for pass B
-            int dq = qs - pqe, dt = ts - pte;
-            dt = dt < 0 ? 0 : dt;
-            dq = dq < 0 ? 0 : dq;
-            const uint32_t which = dt == 0 ? 0u : (dq == 0 ? 1u : 2u);
-            const bool gapped = ok && !isHead && !joined;
-            const uint32_t gapV = gapped ? (uint32_t)dq + (uint32_t)dt : 0u;      // one of them is 0 unless which == 2
-            flag |= ok && !isHead && joined ? 4u : 0u;
-            flag |= gapped ? which << 4 : 0u;
-            sFlag[v] = (unsigned char)flag;
-            sStage[warp][sub * 32 + lane] = StageRec{tW, qW, n | (misc << 20), gapV};
-        }
-        if (errAcc) atomicOr(P.err, errAcc);
-    }
-#if GAT_PASSB_PAIR
-    // pass B, two sub-tiles at a time in straight-line code: loads of both first, rare cases last
-#pragma unroll 1
-    for (int sp = 0; sp < BPT; sp += 2) {
-        StageRec d[2];
-        uint2 ta[2], tb[2], qa[2], qb[2];
-        uint32_t tN[2], qN[2], flag[2];
-        int gDense[2];
-        bool slow[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int v = (warp * BPT + sp + u) * 32 + lane;
-            d[u] = sStage[warp][(sp + u) * 32 + lane];            // written by this lane
-            flag[u] = sFlag[v];
-            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20;
-            // window words (blocks without bases read the front padding)
-            ta[u] = __ldg(P.t.planes + d[u].tW); tb[u] = __ldg(P.t.planes + d[u].tW + 1);
-            qa[u] = __ldg(P.q.planes + d[u].qW); qb[u] = __ldg(P.q.planes + d[u].qW + 1);
-            // N summaries of both windows: one word each unless the window crosses an 8 kb line
-            const uint32_t span = n ? n - 1 : 0u;
-            const uint32_t tw0 = d[u].tW >> 3, tw1 = (d[u].tW + (((misc & 31u) + span) >> 5)) >> 3;
-            const uint32_t qw0 = d[u].qW >> 3, qw1 = (d[u].qW + ((((misc >> 5) & 31u) + span) >> 5)) >> 3;
-            tN[u] = __ldg(P.t.nwin + (tw0 >> 5)) & (0xffffffffu << (tw0 & 31)) & (0xffffffffu >> (31 - (tw1 & 31)));
-            qN[u] = __ldg(P.q.nwin + (qw0 >> 5)) & (0xffffffffu << (qw0 & 31)) & (0xffffffffu >> (31 - (qw1 & 31)));
-            slow[u] = (tw0 >> 5) != (tw1 >> 5) || (qw0 >> 5) != (qw1 >> 5);
-            // gap cost: shared table below smallSize, dense table in L2 up to the last knot
-            const uint32_t gv = d[u].excl;
-            gDense[u] = 0;
-            if (gv >= (uint32_t)P.gap.smallSize && gv < (uint32_t)P.gap.denseSize)
-                gDense[u] = __ldg(P.gapDense + (size_t)((flag[u] >> 4) & 3u) * P.gap.denseSize + gv);
-        }
-        int score[2], gap[2];
-        bool mayN[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20, tSh = misc, qSh = misc >> 5;
-            const uint32_t gv = d[u].excl, which = (flag[u] >> 4) & 3u;
-            const uint32_t sIdx = gv < (uint32_t)P.gap.smallSize ? gv : 0u;
-            const int gSm = gSmall[which * P.gap.smallSize + sIdx];
-            gap[u] = gv < (uint32_t)P.gap.smallSize ? gSm : gDense[u];
-            const uint32_t t1 = __funnelshift_r(ta[u].x, tb[u].x, tSh), t0 = __funnelshift_r(ta[u].y, tb[u].y, tSh);
-            const uint32_t q1 = __funnelshift_r(qa[u].x, qb[u].x, qSh), q0 = __funnelshift_r(qa[u].y, qb[u].y, qSh);
-            const int nv = n >= 32 ? 32 : (int)n;
-            score[u] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, shrOnes(32u - (uint32_t)nv), nv);
-            mayN[u] = n && (slow[u] || (tN[u] | qN[u]) != 0);
-        }
-        // rare: N inside a window, a window longer than the summary word, a gap beyond the dense table
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20, tSh = misc, qSh = misc >> 5;
-            if (mayN[u]) {
-                if (slow[u]) mayN[u] = wordsTouchN(P.t.nwin, d[u].tW, d[u].tW + (((tSh & 31u) + n - 1) >> 5)) ||
-                                       wordsTouchN(P.q.nwin, d[u].qW, d[u].qW + (((qSh & 31u) + n - 1) >> 5));
-                if (mayN[u]) {
-                    const uint32_t t1 = __funnelshift_r(ta[u].x, tb[u].x, tSh), t0 = __funnelshift_r(ta[u].y, tb[u].y, tSh);
-                    const uint32_t q1 = __funnelshift_r(qa[u].x, qb[u].x, qSh), q0 = __funnelshift_r(qa[u].y, qb[u].y, qSh);
-                    const uint32_t vmask = shrOnes(n >= 32 ? 0u : 32u - n) & nFreeMask(P.t.nplane, d[u].tW, tSh, P.q.nplane, d[u].qW, qSh);
-                    score[u] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, __popc(vmask));
-                }
+            // gap in front of the block (gapCalcCost, gapCalc.c:298-331)
+            int gap = 0;
+            if (ok && !isHead) {
+                if (joined) flag |= 4u;
+                else gap = gapCost(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, qs - pqe, ts - pte);
             }
-            if ((int)d[u].excl < 0 || d[u].excl >= (uint32_t)P.gap.denseSize)
-                gap[u] = gapCostOf(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, (flag[u] >> 4) & 3u, d[u].excl);
-        }
-        __syncwarp();
-        // what is left of a block joins the warp's item list, compacted in place: a slot index never
-        // exceeds the position its block had, and every lane has read its descriptor by now
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int v = (warp * BPT + sp + u) * 32 + lane;
-            const uint32_t n = d[u].nMisc & 0xfffffu, misc = d[u].nMisc >> 20;
-            sScore[v] = score[u];
-            sGap[v] = gap[u];
-            anyN |= mayN[u];
+            sGap[v] = gap;
+            sFlag[v] = (unsigned char)flag;
+            const uint32_t t1 = __funnelshift_r(ta.x, tb.x, tSh), t0 = __funnelshift_r(ta.y, tb.y, tSh);
+            const uint32_t q1 = __funnelshift_r(qa.x, qb.x, qSh), q0 = __funnelshift_r(qa.y, qb.y, qSh);
+            int nv = n >= 32 ? 32 : (int)n;
+            uint32_t vmask = shrOnes(32u - (uint32_t)nv);
+            if (mayN) {
+                vmask &= nFreeMask(P.t.nplane, tW, tSh, P.q.nplane, qW, qSh);
+                nv = __popc(vmask);
+            }
+            sScore[v] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
+            anyN |= mayN;
+            // what is left of the block joins the warp's item list
             const bool listed = n > 32;
             const uint32_t lb = __ballot_sync(FULL, listed);
             if (listed) {
                 const int slot = nSlots + __popc(lb & (leMask >> 1));
-                sStage[warp][slot] = StageRec{d[u].tW + 1, d[u].qW + 1, (n - 32) | ((misc | (mayN[u] ? 0x800u : 0u)) << 20), (n - 1) >> 5};   // excl = item count for now
-                sSlotV[warp * TILE + slot] = (unsigned char)((sp + u) * 32 + lane);
+                sStage[warp][slot] = StageRec{tW + 1, qW + 1, (n - 32) | ((tSh | (qSh << 5) | (mayN ? 0x800u : 0u)) << 20), 0u};
+                sEx[warp * TILE + slot] = (n - 1) >> 5;             // item count for now
+                sSlotV[warp * TILE + slot] = (unsigned char)(sub * 32 + lane);
             }
             nSlots += __popc(lb);
         }
+        if (errAcc) atomicOr(P.err, errAcc);
     }
-#else
-    // pass B
-#pragma unroll P1_UNROLL
-    for (int sub = 0; sub < BPT; sub++) {
-        const int v = (warp * BPT + sub) * 32 + lane;
-        const StageRec d = sStage[warp][sub * 32 + lane];      // written by this lane
-        const uint32_t n = d.nMisc & 0xfffffu, misc = d.nMisc >> 20, tSh = misc, qSh = misc >> 5;
-        const uint32_t flag = sFlag[v];
-        // window words (blocks without bases read the front padding) and the N summaries of both windows
-        const uint2 ta = __ldg(P.t.planes + d.tW), tb = __ldg(P.t.planes + d.tW + 1);
-        const uint2 qa = __ldg(P.q.planes + d.qW), qb = __ldg(P.q.planes + d.qW + 1);
-        bool mayN = false;
-        if (n) mayN = wordsTouchN(P.t.nwin, d.tW, d.tW + (((tSh & 31u) + n - 1) >> 5)) ||
-                      wordsTouchN(P.q.nwin, d.qW, d.qW + (((qSh & 31u) + n - 1) >> 5));
-        sGap[v] = gapCostOf(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, (flag >> 4) & 3u, d.excl);
-        const uint32_t t1 = __funnelshift_r(ta.x, tb.x, tSh), t0 = __funnelshift_r(ta.y, tb.y, tSh);
-        const uint32_t q1 = __funnelshift_r(qa.x, qb.x, qSh), q0 = __funnelshift_r(qa.y, qb.y, qSh);
-        int nv = n >= 32 ? 32 : (int)n;
-        uint32_t vmask = shrOnes(32u - (uint32_t)nv);
-        if (mayN) {
-            vmask &= nFreeMask(P.t.nplane, d.tW, tSh, P.q.nplane, d.qW, qSh);
-            nv = __popc(vmask);
-        }
-        sScore[v] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
-        anyN |= mayN;
-        // what is left of the block joins the warp's item list, compacted in place: a slot index never
-        // exceeds the position its block had, and every lane has read its descriptor by now
-        const bool listed = n > 32;
-        const uint32_t lb = __ballot_sync(FULL, listed);
-        __syncwarp();
-        if (listed) {
-            const int slot = nSlots + __popc(lb & (leMask >> 1));
-            sStage[warp][slot] = StageRec{d.tW + 1, d.qW + 1, (n - 32) | ((misc | (mayN ? 0x800u : 0u)) << 20), (n - 1) >> 5};   // excl = item count for now
-            sSlotV[warp * TILE + slot] = (unsigned char)(sub * 32 + lane);
-        }
-        nSlots += __popc(lb);
-    }
-#endif
     anyN = __any_sync(FULL, anyN);
     GAT_TICK(1)
 
@@ -808,20 +654,22 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     const int warpV0 = warp * TILE;
     if (nSlots) {
         uint32_t totalItems;
-        StageRec *st = &sStage[warp][BPT * lane];
+        uint4 *exMine = reinterpret_cast<uint4 *>(&sEx[warpV0 + BPT * lane]);      // my four slots: one 16-byte access, no bank conflicts
         {
+            uint4 ex;
             __syncwarp();
-            const uint32_t c0 = BPT * lane + 0 < nSlots ? st[0].excl : 0u, c1 = BPT * lane + 1 < nSlots ? st[1].excl : 0u;
-            const uint32_t c2 = BPT * lane + 2 < nSlots ? st[2].excl : 0u, c3 = BPT * lane + 3 < nSlots ? st[3].excl : 0u;
+            const uint4 c = *exMine;
+            const uint32_t c0 = BPT * lane + 0 < nSlots ? c.x : 0u, c1 = BPT * lane + 1 < nSlots ? c.y : 0u;
+            const uint32_t c2 = BPT * lane + 2 < nSlots ? c.z : 0u, c3 = BPT * lane + 3 < nSlots ? c.w : 0u;
             uint32_t incl = c0 + c1 + c2 + c3;
             for (int off = 1; off < 32; off <<= 1) {
                 uint32_t o = __shfl_up_sync(FULL, incl, off);
                 if (lane >= off) incl += o;
             }
             totalItems = __shfl_sync(FULL, incl, 31);
-            const uint32_t ex0 = incl - (c0 + c1 + c2 + c3), ex1 = ex0 + c0, ex2 = ex1 + c1, ex3 = ex2 + c2;
-            // slots past the list get excl = totalItems: they never own an item
-            st[0].excl = ex0; st[1].excl = ex1; st[2].excl = ex2; st[3].excl = ex3;
+            ex.x = incl - (c0 + c1 + c2 + c3); ex.y = ex.x + c0; ex.z = ex.y + c1; ex.w = ex.z + c2;
+            *exMine = ex;               // slots past the list get totalItems: they never own an item
+            __syncwarp();
         }
         uint32_t *bits = sBits[warp];
         const uint2 *__restrict__ tPlanes = P.t.planes, *__restrict__ qPlanes = P.q.planes;
@@ -830,11 +678,11 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         for (uint32_t passBase = 0; passBase < totalItems; passBase += PASS_ITEMS) {
             bits[lane] = 0;
             __syncwarp();
-#pragma unroll
-            for (int k = 0; k < BPT; k++) {
-                const uint32_t e = st[k].excl - passBase;
-                if (BPT * lane + k < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31));
-            }
+            const uint4 ex = *exMine;
+            { const uint32_t e = ex.x - passBase; if (BPT * lane + 0 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
+            { const uint32_t e = ex.y - passBase; if (BPT * lane + 1 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
+            { const uint32_t e = ex.z - passBase; if (BPT * lane + 2 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
+            { const uint32_t e = ex.w - passBase; if (BPT * lane + 3 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
             __syncwarp();
             const uint32_t myWord = bits[lane];
             __syncwarp();
@@ -850,7 +698,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
                 OW = before - 1 + __popc(heads & leMask);                                                   \
                 before += __popc(heads);                                                                    \
                 const StageRec rec = sStage[warp][OW];                                                      \
-                const uint32_t k = idx0 + ((uint32_t)(R) << 5) - rec.excl;                                  \
+                const uint32_t k = idx0 + ((uint32_t)(R) << 5) - sEx[warpV0 + OW];                          \
                 MISC = rec.nMisc >> 20;                                                                     \
                 LEFT = (int)(rec.nMisc & 0xfffffu) - (int)(k << 5);                                         \
                 const uint2 *tp = tPlanes + (rec.tW + k);                                                   \
@@ -866,7 +714,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
                 uint32_t vmask = shrOnes(32u - (uint32_t)nv);                                               \
                 if (anyN && (MISC & 0x800u) && nv) {                                                        \
                     const StageRec rec = sStage[warp][OW];                                                  \
-                    const uint32_t k = idx0 + ((uint32_t)(R) << 5) - rec.excl;                              \
+                    const uint32_t k = idx0 + ((uint32_t)(R) << 5) - sEx[warpV0 + OW];                      \
                     vmask &= nFreeMask(P.t.nplane, rec.tW + k, tSh, P.q.nplane, rec.qW + k, qSh);           \
                     nv = __popc(vmask);                                                                     \
                 }                                                                                           \
@@ -895,9 +743,10 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             int prevEnd = __shfl_up_sync(FULL, e4.w, 1);
             if (lane == 0) prevEnd = 0;
             const int d[BPT] = {e4.x - prevEnd, e4.y - e4.x, e4.z - e4.y, e4.w - e4.z};
+            const uint32_t v4 = *reinterpret_cast<const uint32_t *>(&sSlotV[warpV0 + BPT * lane]);
 #pragma unroll
             for (int k = 0; k < BPT; k++)
-                if (BPT * lane + k < nSlots) sScore[warpV0 + sSlotV[warpV0 + BPT * lane + k]] += d[k];
+                if (BPT * lane + k < nSlots) sScore[warpV0 + ((v4 >> (8 * k)) & 0xffu)] += d[k];
         }
     }
     __syncwarp();
@@ -918,10 +767,10 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         for (int k = 0; k < BPT; k++) mag += (long long)(a[k] < 0 ? -(long long)a[k] : (long long)a[k]) + (g[k] < 0 ? -(long long)g[k] : (long long)g[k]);
         const bool small = __all_sync(FULL, mag < (1LL << 22));
         const int wsel = warp * BPT + (lane >> 3);          // bitmap word of my four blocks
-        const uint32_t myWr = __shfl_sync(FULL, wrank, wsel), myHw = sHead[wsel];
-        if (small) warpJobReduce<int>(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
+        const uint32_t myWr = __shfl_sync(FULL, wrank, wsel), myHw = __shfl_sync(FULL, myHeadWord, wsel) & (wsel == 0 ? ~1u : ~0u);
+        if (small) warpJobReduce<int>(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
                                       sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
-        else warpJobReduceWide(P, a, g, fl4, myWr, myHw, sJobSlot, warpV0, vEnd, warp, lane,
+        else warpJobReduceWide(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
                                sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
     }
     GAT_TICK(3)
