@@ -460,9 +460,8 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     else scoreChunksKernel<false><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     {
-        unsigned grid = (unsigned)(((unsigned long long)wl->nChunks * 32 + 255) / 256);
-        fixupKernel<<<grid, 256, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
-                                          wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
+        fixupKernel<<<wl->nChunks, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
+                                                     wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
     }
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaGetLastError());

@@ -803,29 +803,56 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
 
 // ------------------------------------------------------------------ cross-chunk fix-up
 // A job that starts in chunk c and ends in chunk c' > c:  tail(c) + head(c+1) + ... + head(c').
-// One warp per chunk that has such a tail; lanes fold contiguous slices, then an ordered fold.
-__global__ void fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned long long total,
-                            const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
-                            const int *__restrict__ chunkTailJob, uint32_t nChunks,
-                            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, const int *__restrict__ err)
+// One CTA per chunk; nearly all exit at once (no open tail).  The heads are cut into one contiguous slice
+// per thread, folded in order inside the thread, across the warp, and across the warps.
+constexpr int FIX_TPB = 128;
+__device__ __forceinline__ Tup orderedWarpFold(Tup x, int lane)
 {
-    uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= nChunks || *err) return;
+    for (int off = 1; off < 32; off <<= 1) {
+        const Tup o = tupShfl(x, lane + off < 32 ? lane + off : lane);
+        if (lane + off < 32) x = tupCombine(x, o);
+    }
+    return x;       // lane 0: the fold of all 32, in lane order
+}
+__global__ void __launch_bounds__(FIX_TPB)
+fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned long long total,
+            const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
+            const int *__restrict__ chunkTailJob, uint32_t nChunks,
+            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, const int *__restrict__ err)
+{
+    __shared__ Tup sPart[FIX_TPB / 32];
+    const uint32_t c = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (*err) return;
     const int j = chunkTailJob[c];
     if (j < 0) return;
     const unsigned long long np = info[j + 1].blockPtr;
     const uint32_t cLast = (uint32_t)((np - 1) / CHUNK);
     const uint32_t count = cLast - c;                  // heads to fold: chunks c+1 .. cLast
-    Tup all = chunkTail[c];
-    for (uint32_t base = 0; base < count; base += 32) {           // 32 consecutive heads per step, folded in order
-        Tup x = base + lane < count ? chunkHead[c + 1 + base + lane] : tupIdentity();
-        for (int off = 1; off < 32; off <<= 1) {
-            const Tup o = tupShfl(x, lane + off < 32 ? lane + off : lane);
-            if (lane + off < 32) x = tupCombine(x, o);
+    if (count <= 32) {                                 // the common case: one warp, one head per lane
+        if (warp) return;
+        Tup x = (uint32_t)lane < count ? chunkHead[c + 1 + lane] : tupIdentity();
+        x = orderedWarpFold(x, lane);
+        if (lane == 0) {
+            const Tup all = tupCombine(chunkTail[c], x);
+            outGlobal[j] = all.d;
+            outLocal[j] = finalLocal(all);
         }
-        all = tupCombine(all, x);                                 // lane 0 holds the fold
+        return;
     }
-    if (lane == 0) {
+    const uint32_t per = (count + FIX_TPB - 1) / FIX_TPB;
+    Tup mine = tupIdentity();
+#pragma unroll 4
+    for (uint32_t i = 0; i < per; i++) {
+        const uint32_t idx = (uint32_t)tid * per + i;
+        if (idx < count) mine = tupCombine(mine, chunkHead[c + 1 + idx]);
+    }
+    mine = orderedWarpFold(mine, lane);
+    if (lane == 0) sPart[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        Tup all = chunkTail[c];
+        for (int w = 0; w < FIX_TPB / 32; w++) all = tupCombine(all, sPart[w]);
         outGlobal[j] = all.d;
         outLocal[j] = finalLocal(all);
     }
