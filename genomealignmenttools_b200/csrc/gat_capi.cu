@@ -460,7 +460,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     else scoreChunksKernel<false><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     {
-        fixupKernel<<<wl->nChunks, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
+        fixupKernel<<<(wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
                                                      wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
     }
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));

@@ -24,7 +24,10 @@
 
 namespace gat {
 
-constexpr int TPB = 256;               // threads per CTA
+#ifndef GAT_TPB
+#define GAT_TPB 64
+#endif
+constexpr int TPB = GAT_TPB;           // threads per CTA
 constexpr int WARPS = TPB / 32;
 constexpr int BPT = 4;                 // job-blocks per thread = 32-block tiles per warp
 constexpr int CHUNK = TPB * BPT;       // job-blocks per CTA
@@ -376,7 +379,7 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
 struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 
 #ifndef GAT_MIN_CTAS
-#define GAT_MIN_CTAS 4
+#define GAT_MIN_CTAS 16
 #endif
 #ifndef GAT_P1_UNROLL
 #define GAT_P1_UNROLL 1
@@ -531,13 +534,14 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     const uint32_t vb0 = blockIdx.x * (uint32_t)CHUNK;               // totalJobBlocks < 2^32
     const uint32_t total = (uint32_t)P.totalJobBlocks;
     const int vEnd = (int)(total - vb0 < (uint32_t)CHUNK ? total - vb0 : (uint32_t)CHUNK);   // valid job-blocks of this chunk
-    const uint32_t myHeadWord = __ldg(P.headBits + (size_t)blockIdx.x * (CHUNK / 32) + lane);
+    constexpr int WORDS = CHUNK / 32;   // bitmap words per chunk (<= 32: one per lane; lanes past it see the next chunk's words)
+    const uint32_t myHeadWord = __ldg(P.headBits + (size_t)blockIdx.x * WORDS + lane);
     const uint32_t nextHead0 = __ldg(P.headBits + (size_t)(blockIdx.x + 1) * (CHUNK / 32)) & 1u;
     const uint32_t j0 = __ldg(P.chunkJob + blockIdx.x);
     if (*reinterpret_cast<volatile const int *>(P.err)) return;     // jobPrepKernel rejected the work-list (or met an empty job)
     uint32_t wrank;     // lane i: jobs that start in words 0..i-1 of the chunk, not counting the chunk's first block
     {
-        const uint32_t pc = __popc(lane == 0 ? myHeadWord & ~1u : myHeadWord);
+        const uint32_t pc = lane < WORDS ? __popc(lane == 0 ? myHeadWord & ~1u : myHeadWord) : 0u;
         uint32_t inc = pc;
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, inc, off);
@@ -559,20 +563,32 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     {
         int carryTe = 0, carryQe = 0;   // clipped ends of the previous sub-tile's last block
         int errAcc = 0;
+        // job and record of a sub-tile are fetched while the sub-tile before it is being processed
+        auto fetchRecord = [&](int sub, JobInfo &job, gat_block &rec, uint32_t &bi, bool &ok) {
+            const int wi = warp * BPT + sub;
+            const int v = wi * 32 + lane;
+            const uint32_t hw = __shfl_sync(FULL, myHeadWord, wi) & (wi == 0 ? ~1u : ~0u);
+            const uint32_t wr = __shfl_sync(FULL, wrank, wi);
+            const bool valid = v < vEnd;
+            job = loadInfo(P.info, valid ? wr + __popc(hw & leMask) : j0);
+            bi = vb0 + (uint32_t)v + job.delta;
+            ok = valid && (unsigned long long)bi < P.nBlocks;
+            errAcc |= valid && !ok ? ERR_BLOCKIDX : 0;
+            rec = loadBlock(P.blocks, ok ? bi : 0u);
+        };
+        JobInfo jobN; gat_block recN; uint32_t biN; bool okN;
+        fetchRecord(0, jobN, recN, biN, okN);
 #pragma unroll P1_UNROLL
         for (int sub = 0; sub < BPT; sub++) {
             const int wi = warp * BPT + sub;
             const int v = wi * 32 + lane;
             const uint32_t hw = __shfl_sync(FULL, myHeadWord, wi);
-            const uint32_t hwn = wi + 1 < 32 ? __shfl_sync(FULL, myHeadWord, (wi + 1) & 31) : nextHead0;
-            const uint32_t wr = __shfl_sync(FULL, wrank, wi);
-            const bool valid = v < vEnd;
-            const uint32_t jMine = valid ? wr + __popc(hw & (wi == 0 ? ~1u : ~0u) & leMask) : j0;
-            const JobInfo job = loadInfo(P.info, jMine);
-            const uint32_t bi = vb0 + (uint32_t)v + job.delta;
-            const bool ok = valid && (unsigned long long)bi < P.nBlocks;
-            errAcc |= valid && !ok ? ERR_BLOCKIDX : 0;
-            const gat_block rec = loadBlock(P.blocks, ok ? bi : 0u);
+            const uint32_t hwn = wi + 1 < 32 ? __shfl_sync(FULL, myHeadWord, (wi + 1) & 31) : nextHead0   /* WORDS < 32: lane WORDS holds the next chunk's first word */;
+            const JobInfo job = jobN;
+            const gat_block rec = recN;
+            const uint32_t bi = biN;
+            const bool ok = okN;
+            if (sub + 1 < BPT) fetchRecord(sub + 1, jobN, recN, biN, okN);
             const bool isHead = ((hw >> lane) & 1u) != 0;
             const bool isEnd = ((lane < 31 ? hw >> (lane + 1) : hwn) & 1u) != 0;
             uint32_t flag = v < vEnd ? (8u | (isHead ? 1u : 0u) | (isEnd ? 2u : 0u)) : 0u;
@@ -803,9 +819,10 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
 
 // ------------------------------------------------------------------ cross-chunk fix-up
 // A job that starts in chunk c and ends in chunk c' > c:  tail(c) + head(c+1) + ... + head(c').
-// One CTA per chunk; nearly all exit at once (no open tail).  The heads are cut into one contiguous slice
-// per thread, folded in order inside the thread, across the warp, and across the warps.
-constexpr int FIX_TPB = 128;
+// One thread per chunk.  Most open tails end within a few chunks: the thread folds those itself.  A job
+// that runs over many chunks is folded by the whole CTA, one contiguous slice of heads per thread.
+constexpr int FIX_TPB = 256;
+constexpr uint32_t FIX_SERIAL = 16;
 __device__ __forceinline__ Tup orderedWarpFold(Tup x, int lane)
 {
     for (int off = 1; off < 32; off <<= 1) {
@@ -814,47 +831,72 @@ __device__ __forceinline__ Tup orderedWarpFold(Tup x, int lane)
     }
     return x;       // lane 0: the fold of all 32, in lane order
 }
+__device__ __forceinline__ Tup loadTup(const Tup *p)
+{
+    const longlong2 a = *reinterpret_cast<const longlong2 *>(p), b = *(reinterpret_cast<const longlong2 *>(p) + 1);
+    return Tup{a.x, a.y, b.x, b.y};
+}
+// heads[first .. first+n) folded in order; four loads in flight at a time
+__device__ __forceinline__ Tup foldSlice(const Tup *__restrict__ heads, uint32_t first, uint32_t n)
+{
+    Tup acc = tupIdentity();
+    for (uint32_t i = 0; i < n; i += 4) {
+        Tup t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = loadTup(heads + first + (i + k < n ? i + k : i));
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i + k < n) acc = tupCombine(acc, t[k]);
+    }
+    return acc;
+}
 __global__ void __launch_bounds__(FIX_TPB)
 fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned long long total,
             const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
             const int *__restrict__ chunkTailJob, uint32_t nChunks,
             long long *__restrict__ outGlobal, long long *__restrict__ outLocal, const int *__restrict__ err)
 {
+    __shared__ uint32_t sLongC[FIX_TPB], sLongN[FIX_TPB];
+    __shared__ int sLongJ[FIX_TPB];
+    __shared__ int sNLong;
     __shared__ Tup sPart[FIX_TPB / 32];
-    const uint32_t c = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = blockIdx.x * FIX_TPB + tid;
     if (*err) return;
-    const int j = chunkTailJob[c];
-    if (j < 0) return;
-    const unsigned long long np = info[j + 1].blockPtr;
-    const uint32_t cLast = (uint32_t)((np - 1) / CHUNK);
-    const uint32_t count = cLast - c;                  // heads to fold: chunks c+1 .. cLast
-    if (count <= 32) {                                 // the common case: one warp, one head per lane
-        if (warp) return;
-        Tup x = (uint32_t)lane < count ? chunkHead[c + 1 + lane] : tupIdentity();
-        x = orderedWarpFold(x, lane);
-        if (lane == 0) {
-            const Tup all = tupCombine(chunkTail[c], x);
+    if (tid == 0) sNLong = 0;
+    __syncthreads();
+    int j = -1;
+    uint32_t count = 0;                                 // heads to fold: chunks c+1 .. c+count
+    if (c < nChunks) {
+        j = chunkTailJob[c];
+        if (j >= 0) count = (uint32_t)((info[j + 1].blockPtr - 1) / CHUNK) - c;
+    }
+    if (j >= 0) {
+        if (count <= FIX_SERIAL) {
+            const Tup all = tupCombine(loadTup(chunkTail + c), foldSlice(chunkHead, c + 1, count));
             outGlobal[j] = all.d;
             outLocal[j] = finalLocal(all);
+        } else {
+            const int k = atomicAdd(&sNLong, 1);
+            sLongC[k] = c; sLongN[k] = count; sLongJ[k] = j;
         }
-        return;
     }
-    const uint32_t per = (count + FIX_TPB - 1) / FIX_TPB;
-    Tup mine = tupIdentity();
-#pragma unroll 4
-    for (uint32_t i = 0; i < per; i++) {
-        const uint32_t idx = (uint32_t)tid * per + i;
-        if (idx < count) mine = tupCombine(mine, chunkHead[c + 1 + idx]);
-    }
-    mine = orderedWarpFold(mine, lane);
-    if (lane == 0) sPart[warp] = mine;
     __syncthreads();
-    if (tid == 0) {
-        Tup all = chunkTail[c];
-        for (int w = 0; w < FIX_TPB / 32; w++) all = tupCombine(all, sPart[w]);
-        outGlobal[j] = all.d;
-        outLocal[j] = finalLocal(all);
+    const int nLong = sNLong;
+    for (int e = 0; e < nLong; e++) {
+        const uint32_t cc = sLongC[e], n = sLongN[e];
+        const uint32_t per = (n + FIX_TPB - 1) / FIX_TPB;
+        const uint32_t first = (uint32_t)tid * per;
+        Tup mine = foldSlice(chunkHead, cc + 1 + first, first < n ? (n - first < per ? n - first : per) : 0u);
+        mine = orderedWarpFold(mine, lane);
+        if (lane == 0) sPart[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            Tup all = loadTup(chunkTail + cc);
+            for (int w = 0; w < FIX_TPB / 32; w++) all = tupCombine(all, sPart[w]);
+            outGlobal[sLongJ[e]] = all.d;
+            outLocal[sLongJ[e]] = finalLocal(all);
+        }
+        __syncthreads();
     }
 }
 
