@@ -7,16 +7,17 @@
 //
 // HBM layout of a genome ("bit-sliced 2-bit"): 32 consecutive bases are one uint2 = {word of high
 // bits, word of low bits} of the kent base code T=0 C=1 A=2 G=3; base p sits at bit p%32.  So 32
-// aligned bases are ONE 8-byte load, 128 bases are one 32-byte DRAM sector, complement is "flip
-// the high word", reverse is __brev, and an unaligned 32-base window is a funnel shift over two
-// neighbouring uint2.  A third, separate plane holds N (1 bit/base) and is only read for blocks
-// whose 256-base windows contain N.
+// aligned bases are ONE 8-byte load, 128 bases are one 32-byte DRAM sector, and an unaligned 32-base
+// window is a funnel shift over two neighbouring uint2.  The query is resident twice: forward and
+// reverse-complemented (revCompKernel), so a '-' chain reads forward in its own coordinates and the
+// scoring kernel has no strand logic.  A third, separate plane holds N (1 bit/base) and is only read for
+// blocks whose 256-base windows contain N.
 //
-// Work decomposition: the job-blocks of all jobs form one virtual array; a CTA owns CHUNK
-// consecutive job-blocks.  Inside a warp 32 blocks are expanded into 32-base "items" and the
-// items -- not the blocks -- are dealt to lanes, so a 30 kb block and a 5 bp block cost what
-// their bases cost.  Per-block sums come back through one warp scan; per-job global and local
-// scores are a segmented, ordered reduction of a 4-number max-plus tuple (see Tup).
+// Work decomposition: the job-blocks of all jobs form one virtual array; a CTA owns CHUNK consecutive
+// job-blocks, a warp 128 of them.  The first 32 bases of every block are scored lane = block; what is
+// left is expanded into 32-base "items" and the items -- not the blocks -- are dealt to lanes, so a
+// 30 kb block and a 40 bp block cost what their bases cost.  Per-job global and local scores are a
+// segmented, ordered reduction of a 4-number max-plus tuple (see Tup).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
