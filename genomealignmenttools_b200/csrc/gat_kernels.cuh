@@ -386,7 +386,7 @@ struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 #define GAT_P1_UNROLL 1
 #endif
 #ifndef GAT_PREFETCH
-#define GAT_PREFETCH 1      // bit 0: first genome sectors of each block, from phase 1
+#define GAT_PREFETCH 2      // bit 1: fetch the next sub-tile's job and record while the current one is processed
 #endif
 constexpr int P1_UNROLL = GAT_P1_UNROLL;   // sub-tiles of phase 1 in flight per warp
 constexpr int TILE = 32 * BPT;             // job-blocks per warp
@@ -577,19 +577,26 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             errAcc |= valid && !ok ? ERR_BLOCKIDX : 0;
             rec = loadBlock(P.blocks, ok ? bi : 0u);
         };
+#if GAT_PREFETCH & 2
         JobInfo jobN; gat_block recN; uint32_t biN; bool okN;
         fetchRecord(0, jobN, recN, biN, okN);
+#endif
 #pragma unroll P1_UNROLL
         for (int sub = 0; sub < BPT; sub++) {
             const int wi = warp * BPT + sub;
             const int v = wi * 32 + lane;
             const uint32_t hw = __shfl_sync(FULL, myHeadWord, wi);
             const uint32_t hwn = wi + 1 < 32 ? __shfl_sync(FULL, myHeadWord, (wi + 1) & 31) : nextHead0   /* WORDS < 32: lane WORDS holds the next chunk's first word */;
+#if GAT_PREFETCH & 2
             const JobInfo job = jobN;
             const gat_block rec = recN;
             const uint32_t bi = biN;
             const bool ok = okN;
             if (sub + 1 < BPT) fetchRecord(sub + 1, jobN, recN, biN, okN);
+#else
+            JobInfo job; gat_block rec; uint32_t bi; bool ok;
+            fetchRecord(sub, job, rec, bi, ok);
+#endif
             const bool isHead = ((hw >> lane) & 1u) != 0;
             const bool isEnd = ((lane < 31 ? hw >> (lane + 1) : hwn) & 1u) != 0;
             uint32_t flag = v < vEnd ? (8u | (isHead ? 1u : 0u) | (isEnd ? 2u : 0u)) : 0u;

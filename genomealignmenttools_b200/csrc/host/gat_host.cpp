@@ -1,6 +1,7 @@
 // gat_host.cpp -- see gat_host.hpp.  Compiled with -ffp-contract=off: the small gap tables are
 // built with the same double arithmetic, in the same order, as kent/src/lib/gapCalc.c:82-104.
 #include "gat_host.hpp"
+#include <time.h>
 #include <algorithm>
 #include <cctype>
 #include <climits>
@@ -18,6 +19,18 @@ namespace gathost {
 
 // ------------------------------------------------------------------ errAbort / verbose
 static int g_verbose = 1;
+void phaseDone(const char *what)
+{
+    static const bool on = getenv("GAT_TOOL_TIMING") != nullptr;
+    static struct timespec last = {0, 0};
+    if (!on) return;
+    struct timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    if (last.tv_sec || last.tv_nsec)
+        fprintf(stderr, "[timing] %-28s %8.3f s\n", what, (double)(now.tv_sec - last.tv_sec) + 1e-9 * (double)(now.tv_nsec - last.tv_nsec));
+    last = now;
+}
+
 void verboseSetLevel(int level) { g_verbose = level; }
 int verboseLevel() { return g_verbose; }
 
@@ -55,7 +68,10 @@ void fail(const char *fmt, ...)
 int runTool(int (*toolMain)(int, char **), int argc, char **argv)
 {
     try {
-        return toolMain(argc, argv);
+        const int rc = toolMain(argc, argv);
+        // like the kent tools nothing is torn down at the end: flush and leave (skips the CUDA context teardown)
+        fflush(nullptr);
+        _exit(rc);
     } catch (const Error &e) {
         errAbort("%s", e.message.c_str());
     }
@@ -616,18 +632,38 @@ void readChains(const std::string &path, ChainSet &out)
     }
 }
 
+static inline char *putInt(char *p, int v)
+{   // "%d"
+    unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+    char tmp[12];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *p++ = '-';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
 void writeChain(FILE *f, const ChainHead &c, const gat_block *blocks)
-{   // chainWriteHead + chainWrite, chain.c:200-227
+{   // chainWriteHead + chainWrite, chain.c:200-227.  Block lines are formatted by hand into a buffer:
+    // after the GPU has scored a file, fprintf per block would be the longest phase of scoreChain.
     fprintf(f, "chain %1.0f %s %d + %d %d %s %d %c %d %d %d\n", c.score, c.tName.c_str(), c.tSize, c.tStart, c.tEnd,
             c.qName.c_str(), c.qSize, c.qStrand, c.qStart, c.qEnd, c.id);
     const gat_block *b = blocks + c.firstBlock;
+    char buf[1 << 16];
+    char *p = buf;
     for (uint64_t i = 0; i < c.nBlocks; i++) {
-        fprintf(f, "%d", (int)b[i].size);
-        if (i + 1 < c.nBlocks)
-            fprintf(f, "\t%d\t%d", b[i + 1].tStart - (b[i].tStart + (int)b[i].size), b[i + 1].qStart - (b[i].qStart + (int)b[i].size));
-        fputc('\n', f);
+        if (p > buf + sizeof buf - 64) { fwrite(buf, 1, (size_t)(p - buf), f); p = buf; }
+        p = putInt(p, (int)b[i].size);
+        if (i + 1 < c.nBlocks) {
+            *p++ = '\t';
+            p = putInt(p, b[i + 1].tStart - (b[i].tStart + (int)b[i].size));
+            *p++ = '\t';
+            p = putInt(p, b[i + 1].qStart - (b[i].qStart + (int)b[i].size));
+        }
+        *p++ = '\n';
     }
-    fputc('\n', f);
+    *p++ = '\n';
+    fwrite(buf, 1, (size_t)(p - buf), f);
 }
 
 // ------------------------------------------------------------------ work-list
@@ -769,6 +805,32 @@ MultiGpu::MultiGpu(int nGpus)
 MultiGpu::~MultiGpu()
 {
     for (gat_ctx *c : ctx) gat_destroy(c);
+}
+
+// CUDA context creation takes most of a second: tools start it first and parse their inputs meanwhile.
+struct GpuStarter::Impl {
+    std::thread th;
+    MultiGpu *gpus = nullptr;
+    std::string error;
+};
+GpuStarter::GpuStarter(int nGpus) : impl(new Impl)
+{
+    Impl *im = impl;
+    im->th = std::thread([im, nGpus]() {
+        try { im->gpus = new MultiGpu(nGpus); } catch (const Error &e) { im->error = e.message; }
+    });
+}
+MultiGpu &GpuStarter::get()
+{
+    if (impl->th.joinable()) impl->th.join();
+    if (!impl->gpus) fail("%s", impl->error.c_str());
+    return *impl->gpus;
+}
+GpuStarter::~GpuStarter()
+{
+    if (impl->th.joinable()) impl->th.join();
+    // the contexts are left to process exit on purpose (tools leave through _exit, see runTool)
+    delete impl;
 }
 
 void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local)

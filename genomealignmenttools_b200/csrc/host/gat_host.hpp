@@ -19,6 +19,8 @@ namespace gathost {
 [[noreturn]] void errAbort(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 void verbose(int level, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 void verboseSetLevel(int level);
+// GAT_TOOL_TIMING=1 in the environment: wall clock of each phase of a tool on stderr
+void phaseDone(const char *what);
 int verboseLevel();
 // Library code throws; tools call runTool() which turns an Error into errAbort.
 struct Error { std::string message; };
@@ -139,6 +141,15 @@ struct MultiGpu {
     explicit MultiGpu(int nGpus);
     ~MultiGpu();
     void score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local);
+};
+
+// Starts creating the CUDA contexts on a background thread; get() waits for them.
+struct GpuStarter {
+    struct Impl;
+    Impl *impl;
+    explicit GpuStarter(int nGpus);
+    ~GpuStarter();
+    MultiGpu &get();
 };
 
 }  // namespace gathost

@@ -70,13 +70,17 @@ static int toolMain(int argc, char **argv)
     if (access(q2bit, F_OK) != 0) errAbort("ERROR: query 2bit file or nib directory %s does not exist\n", q2bit);
     if (!TwoBitFile::isTwoBit(t2bit)) errAbort("ERROR: only 2bit files are supported, not %s\n", t2bit);
     if (!TwoBitFile::isTwoBit(q2bit)) errAbort("ERROR: only 2bit files are supported, not %s\n", q2bit);
+    phaseDone("start");
+    GpuStarter gpuStarter(opt.intVal("gpus", 1));      // contexts come up while the inputs are parsed
     TwoBitFile tbT(t2bit), tbQ(q2bit);
+    phaseDone("2bit indexes");
 
     FILE *f = strcmp(argv[4], "stdout") == 0 ? stdout : fopen(argv[4], "w");
     if (!f) errAbort("mustOpen: Can't open %s to write: %s", argv[4], strerror(errno));
 
     ChainSet cs;
     readChains(argv[1], cs);
+    phaseDone("chain file parsed");
 
     // like the reference (loadSeq, scoreChain.c:100-116) only sequences that chains name are loaded
     std::vector<int> useT, useQ, mapT(tbT.seqs().size(), -1), mapQ(tbQ.seqs().size(), -1);
@@ -97,15 +101,19 @@ static int toolMain(int argc, char **argv)
     std::vector<int64_t> global, local;
     WorkList wl;
     if (!cs.chains.empty()) {
-        MultiGpu gpus(opt.intVal("gpus", 1));
+        MultiGpu &gpus = gpuStarter.get();
+        phaseDone("CUDA contexts");
         for (gat_ctx *ctx : gpus.ctx) {
             uploadGenome(ctx, GAT_TARGET, tbT, useT);
             uploadGenome(ctx, GAT_QUERY, tbQ, useQ);
             setScoring(ctx, scheme, gapCalc);
         }
+        phaseDone("genomes uploaded");
         buildRecords(cs, wl);
         for (size_t c = 0; c < cs.chains.size(); c++) addChainJob(cs, c, chainT[c], chainQ[c], wl);
+        phaseDone("work-list built");
         gpus.score(wl, global, local);
+        phaseDone("scored on the GPU");
     }
 
     for (size_t c = 0; c < cs.chains.size(); c++) {
@@ -128,6 +136,7 @@ static int toolMain(int argc, char **argv)
         else writeChain(f, h, cs.blocks.data());
     }
     if (f != stdout && fclose(f) != 0) errAbort("Error closing %s", argv[4]);
+    phaseDone("output written");
     return 0;
 }
 

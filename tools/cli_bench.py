@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Tool-level wall clock: the unmodified reference scoreChain (oracle/_ref/scoreChain, one host core, as shipped)
+against the drop-in bin/scoreChain on the SAME files in the same run ("end-to-end tool wall").
+BASELINE.json configs[0]-style input: chains of hg38 chr1 against mm10 chromosomes, synthetic .2bit genomes at the
+real chromosome sizes, default matrix, -linearGap=medium.  Prints one JSON line; the output files must be identical.
+
+usage: tools/cli_bench.py [--blocks 2000000] [--qchroms 8] [--keep DIR]"""
+import argparse
+import filecmp
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+from genomealignmenttools_b200 import synth  # noqa: E402
+import make_golden_helpers as helpers  # noqa: E402
+
+
+def write_chains_fast(path, heads, blocks, first, counts):
+    """chainWrite (chain.c:211-227), vectorised: one text blob per chain would be slow at millions of blocks."""
+    ts = blocks["tStart"].astype(np.int64); qs = blocks["qStart"].astype(np.int64); sz = blocks["size"].astype(np.int64)
+    dt = np.zeros(len(blocks), dtype=np.int64); dq = np.zeros(len(blocks), dtype=np.int64)
+    dt[:-1] = ts[1:] - (ts[:-1] + sz[:-1]); dq[:-1] = qs[1:] - (qs[:-1] + sz[:-1])
+    with open(path, "w") as f:
+        for c, h in enumerate(heads):
+            f.write("chain %.0f %s %d + %d %d %s %d %s %d %d %d\n" % ((h[0],) + tuple(h[1:])))
+            fb, nb = int(first[c]), int(counts[c])
+            if nb > 1:
+                body = np.stack([sz[fb:fb + nb - 1], dt[fb:fb + nb - 1], dq[fb:fb + nb - 1]], axis=1)
+                f.write("\n".join("%d\t%d\t%d" % tuple(r) for r in body.tolist()))
+                f.write("\n")
+            f.write("%d\n\n" % sz[fb + nb - 1])
+
+
+def timed(cmd):
+    t0 = time.time()
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    dt = time.time() - t0
+    if r.returncode != 0:
+        sys.stderr.write(r.stderr.decode()[-2000:])
+        raise SystemExit("%s failed with %d" % (cmd[0], r.returncode))
+    return dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--blocks", type=int, default=2_000_000)
+    ap.add_argument("--qchroms", type=int, default=8, help="mm10 chromosomes the chains land on")
+    ap.add_argument("--keep", default=None)
+    args = ap.parse_args()
+    ex = os.path.join(ROOT, "tests", "golden", "example")
+    tn, ts = synth.read_chrom_sizes(os.path.join(ex, "hg38.chrom.sizes"))
+    qn, qs = synth.read_chrom_sizes(os.path.join(ex, "mm10.chrom.sizes"))
+    tn, ts = tn[:1], ts[:1]                                   # chr1
+    qn, qs = qn[:args.qchroms], qs[:args.qchroms]
+    t0 = time.time()
+    w = synth.make_workload(tn, ts, qn, qs, args.blocks, seed=0x5EED0010, telomere_n=10000, n_fraction=0.001)
+    d = args.keep or tempfile.mkdtemp(prefix="gat_cli_")
+    os.makedirs(d, exist_ok=True)
+    paths = helpers.write_genomes(w, d)
+    heads, counts = helpers.chain_headers(w, tn, qn)
+    write_chains_fast(paths["chain"], heads, w.blocks, w.jobs["firstBlock"], counts)
+    sys.stderr.write("inputs written in %.1f s: %d chains, %d blocks, %.1f Mbp aligned\n"
+                     % (time.time() - t0, len(w.jobs), w.total, w.aligned_bp / 1e6))
+    ref = os.path.join(ROOT, "oracle", "_ref", "scoreChain")
+    ours = os.path.join(ROOT, "bin", "scoreChain")
+    common = [paths["chain"], paths["t"], paths["q"]]
+    out_ref, out_ours = os.path.join(d, "ref.chain"), os.path.join(d, "ours.chain")
+    t_ref = min(timed([ref] + common + [out_ref, "-linearGap=medium"]) for _ in range(2))
+    # CUDA context creation (0.3 .. 2 s on a box without nvidia-persistenced) is part of every run of ours
+    t_ours = min(timed([ours] + common + [out_ours, "-linearGap=medium"]) for _ in range(3))
+    env = dict(os.environ, GAT_TOOL_TIMING="1")
+    phases = subprocess.run([ours] + common + [out_ours, "-linearGap=medium"], stderr=subprocess.PIPE, env=env).stderr.decode()
+    sys.stderr.write(phases)
+    phase_s = {" ".join(l.split()[1:-2]): float(l.split()[-2]) for l in phases.splitlines() if l.startswith("[timing]")}
+    same = filecmp.cmp(out_ref, out_ours, shallow=False)
+    print(json.dumps({"tool": "scoreChain", "config": "hg38 chr1 x mm10 (%d chromosomes), synthetic 2bit, default matrix, linearGap medium" % args.qchroms,
+                      "chains": int(len(w.jobs)), "blocks": int(w.total), "aligned_mbp": round(w.aligned_bp / 1e6, 1),
+                      "reference_wall_s": round(t_ref, 2), "reference_cores": 1, "ours_wall_s": round(t_ours, 2),
+                      "speedup": round(t_ref / t_ours, 2), "outputs_identical": bool(same), "ours_phases_s": phase_s}))
+    if not same:
+        raise SystemExit("outputs differ")
+
+
+if __name__ == "__main__":
+    main()
