@@ -56,6 +56,8 @@ def load():
     lib.gat_worklist_results.argtypes = [vp, vp, vp, vp]
     lib.gat_worklist_destroy.argtypes = [vp, vp]
     lib.gat_worklist_destroy.restype = None
+    lib.gat_max_record_bases.argtypes = [vp]
+    lib.gat_max_record_bases.restype = ctypes.c_uint32
     lib.gat_synchronize.argtypes = [vp]
     lib.gat_get_stats.argtypes = [vp, ctypes.POINTER(GatStats)]
     lib.gat_set_profiling.argtypes = [vp, i32]

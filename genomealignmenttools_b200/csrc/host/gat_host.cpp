@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
+#include <memory>
 #include <queue>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -303,15 +304,26 @@ void uploadGenome(gat_ctx *ctx, int side, const TwoBitFile &tb, const std::vecto
         total += ((uint64_t)s.size + 3) / 4;
         for (size_t k = 0; k < s.nStart.size(); k++) runs.push_back(gat_nrun{(uint32_t)i, s.nStart[k], s.nLen[k]});
     }
-    // the C ABI wants one buffer: gather the used payloads (pinned, so the H2D copy runs at PCIe rate)
-    uint8_t *staging = static_cast<uint8_t *>(gat_host_alloc(total ? total : 1));
-    if (!staging) fail("%s", gat_last_error());
-    for (size_t i = 0; i < use.size(); i++) {
-        const TwoBitSeq &s = tb.seqs()[use[i]];
-        memcpy(staging + offs[i], s.packed, ((size_t)s.size + 3) / 4);
+    // the C ABI wants one buffer: gather the used payloads, a slice per host thread.  Plain memory: pinning
+    // hundreds of MB for one copy costs more than the staged pageable copy it would save.
+    std::unique_ptr<uint8_t[]> staging(new uint8_t[total ? total : 1]);
+    {
+        unsigned T = std::thread::hardware_concurrency();
+        T = std::max(1u, std::min(T ? T : 1u, std::min(16u, (unsigned)(total >> 24) + 1u)));
+        auto body = [&](unsigned k) {       // bytes [lo, hi) of the gathered buffer
+            const uint64_t lo = total / T * k, hi = k + 1 == T ? total : total / T * (k + 1);
+            for (size_t i = 0; i < use.size(); i++) {
+                const uint64_t b = offs[i], e = offs[i] + ((uint64_t)sizes[i] + 3) / 4;
+                const uint64_t from = std::max(b, lo), to = std::min(e, hi);
+                if (from < to) memcpy(staging.get() + from, tb.seqs()[use[i]].packed + (from - b), (size_t)(to - from));
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < T; k++) th.emplace_back(body, k);
+        body(0);
+        for (auto &t : th) t.join();
     }
-    const int rc = gat_load_genome(ctx, side, staging, total, offs.data(), sizes.data(), (uint32_t)use.size(), runs.data(), runs.size());
-    gat_host_free(staging);
+    const int rc = gat_load_genome(ctx, side, staging.get(), total, offs.data(), sizes.data(), (uint32_t)use.size(), runs.data(), runs.size());
     if (rc != GAT_OK) fail("%s", gat_last_error());
 }
 
@@ -575,13 +587,24 @@ static inline bool parseInt(const char *w, int &out)
     return true;
 }
 
-void readChains(const std::string &path, ChainSet &out)
-{   // chainRead, chain.c:256-346
-    std::string text = slurp(path);
-    LineCursor lc(text);
+// chainRead (chain.c:256-346) over text[begin, end), which starts at a chain header (or at file start).
+// Chains without an id column get id INT_MIN here; readChains numbers them in file order afterwards.
+static void parseChainText(std::string &text, size_t begin, size_t end, int lineBase, bool moreFollows, const char *fn, ChainSet &out)
+{
+    struct Cursor {     // splits [pos, end) into lines in place (replaces '\n' by 0); no copy
+        std::string &text; size_t pos, end; int lineIx;
+        char *next()
+        {
+            if (pos >= end) return nullptr;
+            char *line = &text[pos];
+            const void *nl = memchr(line, '\n', end - pos);
+            if (!nl) { pos = end; if (end < text.size()) text[end] = 0; }
+            else { const size_t at = (size_t)((const char *)nl - text.data()); text[at] = 0; pos = at + 1; }
+            lineIx++;
+            return line;
+        }
+    } lc{text, begin, end, lineBase};
     char *w[16];
-    int nextId = 1;
-    const char *fn = path.c_str();
     auto chopNext = [&](int maxWords) -> int {
         for (char *line; (line = lc.next()) != nullptr;) {
             if (line[0] == '#') { out.metaLines.emplace_back(line); out.metaLineChain.push_back(out.chains.size()); continue; }
@@ -605,7 +628,7 @@ void readChains(const std::string &path, ChainSet &out)
         };
         need(3, c.tSize);
         if (n >= 13) need(12, c.id);
-        else c.id = nextId++;
+        else c.id = INT_MIN;
         need(5, c.tStart); need(6, c.tEnd); need(8, c.qSize); need(10, c.qStart); need(11, c.qEnd);
         if (c.qStart >= c.qEnd || c.tStart >= c.tEnd) fail("End before start line %d of %s", lc.lineIx, fn);
         if (c.qStart < 0 || c.tStart < 0) fail("Start before zero line %d of %s", lc.lineIx, fn);
@@ -614,7 +637,11 @@ void readChains(const std::string &path, ChainSet &out)
         int q = c.qStart, t = c.tStart;
         for (;;) {
             n = chopNext(3);
-            if (n == 0) fail("Unexpected end of file in %s", fn);
+            if (n == 0) {
+                // a piece ends inside a chain only if the next piece's header interrupts it: say what a sequential read says
+                if (moreFollows) fail("Expecting number field 1 line %d of %s, got %s", lc.lineIx + 1, fn, "chain");
+                fail("Unexpected end of file in %s", fn);
+            }
             int size, dt, dq;
             if (!parseInt(w[0], size)) fail("Expecting number field 1 line %d of %s, got %s", lc.lineIx, fn, w[0]);
             out.blocks.push_back(gat_block{t, q, (uint32_t)size});
@@ -630,6 +657,75 @@ void readChains(const std::string &path, ChainSet &out)
         if (t != c.tEnd) fail("t end mismatch %d vs %d line %d of %s\n", t, c.tEnd, lc.lineIx, fn);
         out.chains.push_back(std::move(c));
     }
+}
+
+static unsigned hostThreads(size_t work, size_t perThread)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    if (hw > 32) hw = 32;
+    const size_t want = work / perThread;
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(hw, want));
+}
+
+void readChains(const std::string &path, ChainSet &out)
+{   // The file is cut at chain headers ("\nchain " can only be one: block lines are numbers, meta lines start
+    // with '#') into one piece per host thread; the pieces are parsed concurrently and joined in file order,
+    // so chains, blocks, meta lines, sequential ids and the first error are those of a sequential read.
+    std::string text = slurp(path);
+    const char *fn = path.c_str();
+    // GAT_PARSE_PIECE_BYTES: smallest piece worth a thread (tests set it to a few bytes to cut small files)
+    const char *pieceEnv = getenv("GAT_PARSE_PIECE_BYTES");
+    const unsigned T = hostThreads(text.size(), pieceEnv && atol(pieceEnv) > 0 ? (size_t)atol(pieceEnv) : (size_t)4 << 20);
+    std::vector<size_t> cut(T + 1, text.size());
+    cut[0] = 0;
+    for (unsigned i = 1; i < T; i++) {
+        const size_t from = std::max(cut[i - 1], text.size() / T * i);
+        const size_t at = text.find("\nchain ", from);
+        cut[i] = at == std::string::npos ? text.size() : at + 1;
+    }
+    std::vector<int> lineBase(T + 1, 0);
+    std::vector<ChainSet> part(T);
+    std::vector<std::string> error(T);
+    std::vector<char> failed(T, 0);
+    auto run = [&](auto &&body) {
+        std::vector<std::thread> th;
+        for (unsigned i = 1; i < T; i++) th.emplace_back(body, i);
+        body(0u);
+        for (auto &t : th) t.join();
+    };
+    if (T > 1) {
+        std::vector<int> lines(T, 0);
+        run([&](unsigned i) { lines[i] = (int)std::count(text.begin() + (long)cut[i], text.begin() + (long)cut[i + 1], '\n'); });
+        for (unsigned i = 0; i < T; i++) lineBase[i + 1] = lineBase[i] + lines[i];
+    }
+    run([&](unsigned i) {
+        try { parseChainText(text, cut[i], cut[i + 1], lineBase[i], cut[i + 1] < text.size(), fn, i == 0 ? out : part[i]); }
+        catch (const Error &e) { failed[i] = 1; error[i] = e.message; }
+    });
+    for (unsigned i = 0; i < T; i++)
+        if (failed[i]) fail("%s", error[i].c_str());
+    size_t nChains = out.chains.size(), nBlocks = out.blocks.size();
+    std::vector<size_t> chainAt(T, 0), blockAt(T, 0);
+    for (unsigned i = 1; i < T; i++) { chainAt[i] = nChains; blockAt[i] = nBlocks; nChains += part[i].chains.size(); nBlocks += part[i].blocks.size(); }
+    out.chains.resize(nChains);
+    out.blocks.resize(nBlocks);
+    run([&](unsigned i) {
+        if (i == 0) return;
+        std::copy(part[i].blocks.begin(), part[i].blocks.end(), out.blocks.begin() + (long)blockAt[i]);
+        for (size_t c = 0; c < part[i].chains.size(); c++) {
+            part[i].chains[c].firstBlock += blockAt[i];
+            out.chains[chainAt[i] + c] = std::move(part[i].chains[c]);
+        }
+    });
+    for (unsigned i = 1; i < T; i++)
+        for (size_t m = 0; m < part[i].metaLines.size(); m++) {
+            out.metaLines.push_back(std::move(part[i].metaLines[m]));
+            out.metaLineChain.push_back(part[i].metaLineChain[m] + chainAt[i]);
+        }
+    int nextId = 1;                             // chain.c:276-279
+    for (ChainHead &c : out.chains)
+        if (c.id == INT_MIN) c.id = nextId++;
 }
 
 static inline char *putInt(char *p, int v)
@@ -664,6 +760,60 @@ void writeChain(FILE *f, const ChainHead &c, const gat_block *blocks)
     }
     *p++ = '\n';
     fwrite(buf, 1, (size_t)(p - buf), f);
+}
+
+static void formatChain(std::string &o, const ChainHead &c, const gat_block *blocks)
+{
+    char head[512];
+    const int hn = snprintf(head, sizeof head, "chain %1.0f %s %d + %d %d %s %d %c %d %d %d\n", c.score, c.tName.c_str(), c.tSize,
+                            c.tStart, c.tEnd, c.qName.c_str(), c.qSize, c.qStrand, c.qStart, c.qEnd, c.id);
+    if (hn < 0 || (size_t)hn >= sizeof head) {      // very long sequence names: let the C library size it
+        std::string big((size_t)hn + 1, 0);
+        snprintf(&big[0], big.size(), "chain %1.0f %s %d + %d %d %s %d %c %d %d %d\n", c.score, c.tName.c_str(), c.tSize,
+                 c.tStart, c.tEnd, c.qName.c_str(), c.qSize, c.qStrand, c.qStart, c.qEnd, c.id);
+        o.append(big.c_str());
+    } else o.append(head, (size_t)hn);
+    const gat_block *b = blocks + c.firstBlock;
+    char buf[4096];
+    char *p = buf;
+    for (uint64_t i = 0; i < c.nBlocks; i++) {
+        if (p > buf + sizeof buf - 64) { o.append(buf, (size_t)(p - buf)); p = buf; }
+        p = putInt(p, (int)b[i].size);
+        if (i + 1 < c.nBlocks) {
+            *p++ = '\t';
+            p = putInt(p, b[i + 1].tStart - (b[i].tStart + (int)b[i].size));
+            *p++ = '\t';
+            p = putInt(p, b[i + 1].qStart - (b[i].qStart + (int)b[i].size));
+        }
+        *p++ = '\n';
+    }
+    *p++ = '\n';
+    o.append(buf, (size_t)(p - buf));
+}
+
+void writeChains(FILE *f, const std::vector<ChainHead> &chains, const gat_block *blocks)
+{   // chainWrite for a whole set: pieces of about equal size are formatted on the host threads, written in order
+    uint64_t total = 0;
+    for (const ChainHead &c : chains) total += c.nBlocks + 4;
+    const unsigned T = hostThreads((size_t)total, (size_t)1 << 18);
+    std::vector<size_t> cut(T + 1, chains.size());
+    cut[0] = 0;
+    {
+        uint64_t acc = 0; unsigned k = 1;
+        for (size_t c = 0; c < chains.size() && k < T; c++) {
+            acc += chains[c].nBlocks + 4;
+            if (acc >= total / T * k) cut[k++] = c + 1;
+        }
+    }
+    std::vector<std::string> piece(T);
+    std::vector<std::thread> th;
+    auto body = [&](unsigned i) {
+        for (size_t c = cut[i]; c < cut[i + 1]; c++) formatChain(piece[i], chains[c], blocks);
+    };
+    for (unsigned i = 1; i < T; i++) th.emplace_back(body, i);
+    body(0);
+    for (auto &t : th) t.join();
+    for (unsigned i = 0; i < T; i++) fwrite(piece[i].data(), 1, piece[i].size(), f);
 }
 
 // ------------------------------------------------------------------ work-list

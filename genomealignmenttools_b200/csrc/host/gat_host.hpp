@@ -114,6 +114,7 @@ struct ChainSet {
 // Reads every chain of a file (plain, or .gz through `gzip -dc` like linefile.c:40-53).
 void readChains(const std::string &path, ChainSet &out);
 void writeChain(FILE *f, const ChainHead &c, const gat_block *blocks);     // chainWrite, chain.c:211-227
+void writeChains(FILE *f, const std::vector<ChainHead> &chains, const gat_block *blocks);   // all of them, formatted in parallel
 
 // ---- work-list
 struct WorkList {

@@ -133,8 +133,8 @@ static int toolMain(int argc, char **argv)
         if (returnOnlyScore) fprintf(f, "%d\t%1.0f\t%1.0f\t%d\n", h.id, globalScore, localScore, (int)wl.aliBases[c]);
         else if (returnOnlyScoreAndCoords)
             fprintf(f, "%d\t%d\t%d\t%1.0f\t%1.0f\t%d\n", h.id, h.tStart, h.tEnd, globalScore, localScore, (int)wl.aliBases[c]);
-        else writeChain(f, h, cs.blocks.data());
     }
+    if (!returnOnlyScore && !returnOnlyScoreAndCoords) writeChains(f, cs.chains, cs.blocks.data());
     if (f != stdout && fclose(f) != 0) errAbort("Error closing %s", argv[4]);
     phaseDone("output written");
     return 0;

@@ -85,6 +85,10 @@ class ChainScorer:
     def __exit__(self, *a):
         self.close()
 
+    def max_record_bases(self):
+        """Longest record (gat_block.size) the device accepts under the current scoring parameters."""
+        return int(self.lib.gat_max_record_bases(self.ctx))
+
     def load_genome(self, side, genome):
         """side: 0/'t' target, 1/'q' query; genome: PackedGenome (payload stays packed)."""
         side = {"t": TARGET, "q": QUERY}.get(side, side)

@@ -239,6 +239,37 @@ def test_empty_and_invalid_worklists():
         assert e.value.code == -3
 
 
+def test_record_length_limit_follows_the_matrix(oracle, tmp_path):
+    """32-bit record sums: gat_max_record_bases() = min(2^20-1, (2^31-1)/max|M|), never below GAT_SPLIT_BASES; a record at the
+    limit scores exactly, one past it is rejected, |M| beyond 2^18 is refused by gat_set_scoring."""
+    rng = np.random.default_rng(4)
+    n = 9000
+    codes = rng.integers(0, 4, n)
+    t = PackedGenome.from_codes(["t"], [codes])
+    q = PackedGenome.from_codes(["q"], [codes.copy()])
+    big = Scoring(ScoreScheme(np.array([[250000, -250000, -1, -2], [-250000, 250000, -3, -4], [-1, -3, 250000, -250000],
+                                        [-2, -4, -250000, 250000]], dtype=np.int32)), "loose")
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", t); sc.load_genome("q", q)
+        sc.set_scoring(Scoring(None, "loose"))
+        assert sc.max_record_bases() == (1 << 20) - 1
+        sc.set_scoring(big)
+        lim = sc.max_record_bases()
+        assert lim == (2 ** 31 - 1) // 250000 and lim >= 4096
+        jobs = np.array([(0, 0, 0, 0, NO_CLIP_START, NO_CLIP_END)], dtype=JOB_DTYPE)
+        g, l = sc.score(jobs, 1, np.array([(0, 0, lim)], dtype=BLOCK_DTYPE))
+        assert g[0] == 250000 * lim and l[0] == g[0]                    # identical sequences: every base a match
+        with pytest.raises(GatError):
+            sc.score(jobs, 1, np.array([(0, 0, lim + 1)], dtype=BLOCK_DTYPE))
+        # the same block as JOINED records of GAT_SPLIT_BASES scores as one block and may exceed 32 bits
+        pieces = [(o, o, min(4096, n - o) | (BLOCK_JOINED if o else 0)) for o in range(0, n, 4096)]
+        g, l = sc.score(jobs, len(pieces), np.array(pieces, dtype=BLOCK_DTYPE))
+        assert g[0] == 250000 * n and l[0] == g[0]
+        too_big = Scoring(ScoreScheme(np.full((4, 4), 300000, dtype=np.int32)), "loose")
+        with pytest.raises(GatError):
+            sc.set_scoring(too_big)
+
+
 def test_resident_worklist_matches_one_shot():
     w, _, _ = small_world(seed=12, n_blocks=9000)
     with ChainScorer(0) as sc:

@@ -131,6 +131,48 @@ def test_chain_readers_agree(oracle, golden, rel):
     assert np.array_equal(hostlib.chain_blocks(lib, cs), py.blocks)
 
 
+@pytest.mark.parametrize("piece", ["1", "300", "5000"])
+def test_chain_reader_pieces_parsed_concurrently_equal_sequential(golden, tmp_path, monkeypatch, piece):
+    """readChains cuts the file at chain headers and parses the pieces on host threads; chains, blocks, sequential
+    ids of id-less chains, '#' lines and the first error must be those of a sequential read (GAT_PARSE_PIECE_BYTES
+    forces cuts in small files)."""
+    lib = hostlib.load()
+    src = open(os.path.join(golden, "synth_small", "in.chain")).read().split("\n")
+    lines, k = [], 0
+    for ln in src:
+        if ln.startswith("chain "):
+            k += 1
+            if k % 3 == 0:
+                lines.append("# note before chain %d" % k)
+            if k % 2 == 0:
+                ln = " ".join(ln.split()[:12])          # drop the id column: chain.c:276-279 numbers those
+        lines.append(ln)
+    path = tmp_path / "mixed.chain"
+    path.write_text("\n".join(lines))
+    monkeypatch.delenv("GAT_PARSE_PIECE_BYTES", raising=False)
+    a = lib.gathost_chains_read(str(path).encode())
+    monkeypatch.setenv("GAT_PARSE_PIECE_BYTES", piece)
+    b = lib.gathost_chains_read(str(path).encode())
+    assert a and b
+    assert hostlib.chain_heads(lib, a) == hostlib.chain_heads(lib, b)
+    assert np.array_equal(hostlib.chain_blocks(lib, a), hostlib.chain_blocks(lib, b))
+    # an interrupted chain is reported like a sequential read reports it, whichever piece meets it
+    bad = lines[:]
+    third = [i for i, ln in enumerate(bad) if ln.startswith("chain ")][2]
+    last = max(i for i in range(third) if bad[i] and bad[i][0].isdigit())
+    bad[last] = bad[last] + "\t3\t4"                     # the chain before now expects another block line
+    (tmp_path / "bad.chain").write_text("\n".join(bad))
+    msgs = []
+    for env in (None, piece):
+        if env is None:
+            monkeypatch.delenv("GAT_PARSE_PIECE_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("GAT_PARSE_PIECE_BYTES", env)
+        assert not lib.gathost_chains_read(str(tmp_path / "bad.chain").encode())
+        msgs.append(lib.gathost_last_error())
+    assert msgs[0] == msgs[1] and b"line" in msgs[0]
+
+
 def test_chain_reader_errors(tmp_path):
     lib = hostlib.load()
     good = "chain 100 chrA 1000 + 10 60 chrB 900 - 5 65 7\n20\t10\t20\n20\n\n"
