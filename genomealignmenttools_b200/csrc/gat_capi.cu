@@ -348,6 +348,10 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
     return GAT_OK;
 }
 
+// Words of the job-start bitmap for n chunks: the chunks' own, one chunk of look-ahead (is the block after a chunk's last
+// a job start?), the closing bit, and the 32 words every warp of the last chunk reads (one per lane).
+static size_t headWords(uint64_t nChunks) { return (size_t)(nChunks + 2) * (CHUNK / 32) + 32; }
+
 // Size (or re-size) a work-list's device buffers.  Buffers only ever grow, so a scratch work-list
 // that has seen the largest batch allocates nothing on later calls.
 static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_t totalJobBlocks, uint64_t nBlocks)
@@ -366,7 +370,7 @@ static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_
         CU(cudaMalloc(&wl->info, (cj + 1) * sizeof(JobInfo)));
         if (!wl->borrowedBlocks) CU(cudaMalloc(&wl->blocks, (cb + 1) * sizeof(gat_block)));
         CU(cudaMalloc(&wl->chunkJob, (cc + 1) * sizeof(uint32_t)));
-        CU(cudaMalloc(&wl->headBits, (cc + 2) * (CHUNK / 32) * sizeof(uint32_t)));
+        CU(cudaMalloc(&wl->headBits, headWords(cc) * sizeof(uint32_t)));
         CU(cudaMalloc(&wl->chunkHead, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTail, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTailJob, (cc + 1) * sizeof(int)));
@@ -447,7 +451,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
 
     const bool prof = ctx->profiling;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
-    CU(cudaMemsetAsync(wl->headBits, 0, ((size_t)wl->nChunks + 2) * (CHUNK / 32) * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(wl->headBits, 0, headWords(wl->nChunks) * sizeof(uint32_t), st));
     {
         const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
         unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
