@@ -308,7 +308,8 @@ struct LiveChain {
     ChainHead head;
     std::vector<gat_block> blocks;      // current blocks (suspects get removed)
     uint32_t tSeq = 0, qSeq = 0;
-    int version = 0;                    // bumped whenever blocks are removed
+    std::vector<std::pair<int, int>> removed;   // target ranges whose blocks were removed, in order of removal
+    mutable int monotone = -1;          // blocks ascending and disjoint on the target (-1: not checked yet)
 };
 static std::map<int, LiveChain> live;   // by chain id
 static int maxChainId = -1;
@@ -320,10 +321,22 @@ struct SubSel { bool isNull, whole; size_t first, count; };
 static SubSel selectSub(const LiveChain &c, int subStart, int subEnd)
 {
     if (subStart <= c.head.tStart && subEnd >= c.head.tEnd) return SubSel{c.blocks.empty(), true, 0, c.blocks.size()};
-    size_t a = 0;
-    while (a < c.blocks.size() && c.blocks[a].tStart + (int)c.blocks[a].size <= subStart) a++;
-    size_t e = a;
-    while (e < c.blocks.size() && c.blocks[e].tStart < subEnd) e++;
+    if (c.monotone < 0) {
+        c.monotone = 1;
+        for (size_t i = 1; i < c.blocks.size(); i++)
+            if (c.blocks[i].tStart < c.blocks[i - 1].tStart + (int)c.blocks[i - 1].size) { c.monotone = 0; break; }
+    }
+    size_t a = 0, e;
+    if (c.monotone) {   // the reference walks the list from its head (chain.c:479-510); on sorted blocks a bisection finds the same range
+        a = (size_t)(std::partition_point(c.blocks.begin(), c.blocks.end(),
+                                          [&](const gat_block &b) { return b.tStart + (int)b.size <= subStart; }) - c.blocks.begin());
+        e = (size_t)(std::partition_point(c.blocks.begin() + (long)a, c.blocks.end(),
+                                          [&](const gat_block &b) { return b.tStart < subEnd; }) - c.blocks.begin());
+    } else {
+        while (a < c.blocks.size() && c.blocks[a].tStart + (int)c.blocks[a].size <= subStart) a++;
+        e = a;
+        while (e < c.blocks.size() && c.blocks[e].tStart < subEnd) e++;
+    }
     return SubSel{e == a, false, a, e - a};
 }
 
@@ -357,27 +370,29 @@ public:
     std::vector<SubScore> score(const std::vector<Request> &reqs)
     {
         std::vector<SubScore> out(reqs.size());
-        ChainSet cs;                    // the chains the requests touch, with their current blocks
-        std::map<int, size_t> slot;
-        for (const Request &r : reqs)
-            if (!slot.count(r.chainId)) {
-                const LiveChain &c = live.at(r.chainId);
-                slot[r.chainId] = cs.chains.size();
-                ChainHead h = c.head;
-                h.firstBlock = cs.blocks.size();
-                h.nBlocks = c.blocks.size();
-                cs.blocks.insert(cs.blocks.end(), c.blocks.begin(), c.blocks.end());
-                cs.chains.push_back(h);
-            }
-        WorkList wl;
-        buildRecords(cs, wl);
-        std::vector<size_t> jobOf(reqs.size(), (size_t)-1);
+        // every request becomes a chain of its own holding just the blocks chainSubsetOnT would keep: what is
+        // copied, split into records and uploaded is proportional to the sub-chains, not to the chains they come from
+        ChainSet cs;
+        std::vector<size_t> chainOf(reqs.size(), (size_t)-1);
         for (size_t i = 0; i < reqs.size(); i++) {
             const LiveChain &c = live.at(reqs[i].chainId);
             const SubSel sel = selectSub(c, reqs[i].subStart, reqs[i].subEnd);
             out[i].whole = sel.whole;
             if (sel.isNull) continue;
-            if (!addSubChainJob(cs, slot[reqs[i].chainId], c.tSeq, c.qSeq, reqs[i].subStart, reqs[i].subEnd, wl)) continue;
+            ChainHead h = c.head;
+            h.firstBlock = cs.blocks.size();
+            h.nBlocks = sel.count;
+            cs.blocks.insert(cs.blocks.end(), c.blocks.begin() + (long)sel.first, c.blocks.begin() + (long)(sel.first + sel.count));
+            chainOf[i] = cs.chains.size();
+            cs.chains.push_back(h);
+        }
+        WorkList wl;
+        buildRecords(cs, wl);
+        std::vector<size_t> jobOf(reqs.size(), (size_t)-1);
+        for (size_t i = 0; i < reqs.size(); i++) {
+            if (chainOf[i] == (size_t)-1) continue;
+            const LiveChain &c = live.at(reqs[i].chainId);
+            if (!addSubChainJob(cs, chainOf[i], c.tSeq, c.qSeq, reqs[i].subStart, reqs[i].subEnd, wl)) continue;
             jobOf[i] = wl.jobs.size() - 1;
         }
         std::vector<int64_t> global, local;
@@ -398,22 +413,48 @@ private:
     MultiGpu gpus;
 };
 
-// The four sub-chains of one tested suspect (chainCleaner.c:1214-1217) and what they were scored against
+// The four sub-chains of one tested suspect (chainCleaner.c:1214-1217).  Their scores stay valid until blocks are
+// removed from the breaking chain inside the suspect range, or from the broken chain inside the fill range: a
+// removal elsewhere leaves the blocks chainSubsetOnT selects, and the gaps between them, as they were.
 struct TestKey {
-    int parentId, brokenId, parentVersion, brokenVersion, suspectStart, suspectEnd, LfillStart, RfillEnd;
+    int parentId, brokenId, suspectStart, suspectEnd, LfillStart, RfillEnd;
     bool operator<(const TestKey &o) const
     {
-        return std::tie(parentId, brokenId, parentVersion, brokenVersion, suspectStart, suspectEnd, LfillStart, RfillEnd) <
-               std::tie(o.parentId, o.brokenId, o.parentVersion, o.brokenVersion, o.suspectStart, o.suspectEnd, o.LfillStart, o.RfillEnd);
+        return std::tie(parentId, brokenId, suspectStart, suspectEnd, LfillStart, RfillEnd) <
+               std::tie(o.parentId, o.brokenId, o.suspectStart, o.suspectEnd, o.LfillStart, o.RfillEnd);
     }
 };
-struct TestScores { SubScore suspect, fill, lfill, rfill; };
+struct TestScores {
+    SubScore suspect, fill, lfill, rfill;
+    size_t parentSeen = 0, brokenSeen = 0;      // removals of either chain already reflected in the scores
+    bool scored = false;
+};
 static std::map<TestKey, TestScores> cache;
 
 static TestKey keyOf(const Break &b)
 {
-    return TestKey{b.parentChainId, b.chainId, live.at(b.parentChainId).version, live.at(b.chainId).version, b.suspectStart, b.suspectEnd,
-                   b.LfillStart, b.RfillEnd};
+    return TestKey{b.parentChainId, b.chainId, b.suspectStart, b.suspectEnd, b.LfillStart, b.RfillEnd};
+}
+
+static bool touchedSince(const LiveChain &c, size_t seen, int start, int end)
+{
+    for (size_t i = seen; i < c.removed.size(); i++)
+        if (c.removed[i].first < end && c.removed[i].second > start) return true;
+    return false;
+}
+
+// is the cache entry of this break still what a fresh scoring would give?
+static bool cacheValid(const Break &b)
+{
+    auto it = cache.find(keyOf(b));
+    if (it == cache.end()) return false;
+    TestScores &t = it->second;
+    if (!t.scored) return true;                 // reserved inside the batch being assembled
+    const LiveChain &parent = live.at(b.parentChainId), &broken = live.at(b.chainId);
+    if (touchedSince(parent, t.parentSeen, b.suspectStart, b.suspectEnd) || touchedSince(broken, t.brokenSeen, b.LfillStart, b.RfillEnd)) return false;
+    t.parentSeen = parent.removed.size();
+    t.brokenSeen = broken.removed.size();
+    return true;
 }
 
 static void requestsFor(const Break &b, std::vector<Request> &reqs)
@@ -430,15 +471,22 @@ static void ensureScored(Scorer &scorer, const std::vector<const Break *> &todo)
     std::vector<Request> reqs;
     std::vector<TestKey> keys;
     for (const Break *b : todo) {
+        if (cacheValid(*b)) continue;
         const TestKey k = keyOf(*b);
-        if (cache.count(k)) continue;
-        cache[k];                       // reserve, so duplicates inside this batch are requested once
+        cache[k] = TestScores();        // reserve, so duplicates inside this batch are requested once
         keys.push_back(k);
         requestsFor(*b, reqs);
     }
     if (reqs.empty()) return;
     const std::vector<SubScore> res = scorer.score(reqs);
-    for (size_t i = 0; i < keys.size(); i++) cache[keys[i]] = TestScores{res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]};
+    for (size_t i = 0; i < keys.size(); i++) {
+        TestScores t;
+        t.suspect = res[4 * i]; t.fill = res[4 * i + 1]; t.lfill = res[4 * i + 2]; t.rfill = res[4 * i + 3];
+        t.parentSeen = live.at(keys[i].parentId).removed.size();
+        t.brokenSeen = live.at(keys[i].brokenId).removed.size();
+        t.scored = true;
+        cache[keys[i]] = t;
+    }
 }
 
 // ---------------------------------------------------------------- the suspect loop
@@ -462,7 +510,7 @@ static void chainRemoveBlocks(LiveChain &c, int tStart, int tEnd)
     if (last >= c.blocks.size())
         errAbort("ERROR in chainRemoveBlocks: boundaries imply that we remove the last block of chain Id %d (tStart %d - tEnd %d)\n", c.head.id, tStart, tEnd);
     c.blocks.erase(c.blocks.begin() + first + 1, c.blocks.begin() + last);
-    c.version++;
+    c.removed.emplace_back(tStart, tEnd);
 }
 
 // the sub-chain chainFastSubsetOnT would build (chain.c:490-558), for writing a removed suspect

@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=2_000_000)
     ap.add_argument("--qchroms", type=int, default=8, help="mm10 chromosomes the chains land on")
     ap.add_argument("--keep", default=None)
+    ap.add_argument("--tools", default="scoreChain", help="comma list of scoreChain,chainNet,chainCleaner (configs[0..2] of BASELINE.json)")
     args = ap.parse_args()
     ex = os.path.join(ROOT, "tests", "golden", "example")
     tn, ts = synth.read_chrom_sizes(os.path.join(ex, "hg38.chrom.sizes"))
@@ -86,6 +87,49 @@ def main():
                       "speedup": round(t_ref / t_ours, 2), "outputs_identical": bool(same), "ours_phases_s": phase_s}))
     if not same:
         raise SystemExit("outputs differ")
+    tools = args.tools.split(",")
+    if "chainNet" in tools or "chainCleaner" in tools:
+        refdir, ourdir = os.path.join(ROOT, "oracle", "_ref"), os.path.join(ROOT, "bin")
+        for name, names, sizes in (("t.sizes", tn, ts), ("q.sizes", qn, qs)):
+            with open(os.path.join(d, name), "w") as f:
+                f.write("".join("%s\t%d\n" % p for p in zip(names, sizes)))
+        srt = os.path.join(d, "sorted.chain")
+        subprocess.check_call([os.path.join(refdir, "chainSort"), out_ref, srt])
+        sizes = [os.path.join(d, "t.sizes"), os.path.join(d, "q.sizes")]
+    if "chainNet" in tools:      # configs[1]: chainNet -rescore, every partial fill rescored
+        common = ["-rescore", "-linearGap=medium", "-tNibDir=" + paths["t"], "-qNibDir=" + paths["q"], srt] + sizes
+        nets = {k: [os.path.join(d, "%s.%s.net" % (k, x)) for x in "tq"] for k in ("ref", "our")}
+        t_ref = timed([os.path.join(refdir, "chainNet")] + common + nets["ref"])
+        t_ours = min(timed([os.path.join(ourdir, "chainNet")] + common + nets["our"]) for _ in range(2))
+        same = all(filecmp.cmp(a, b, shallow=False) for a, b in zip(nets["ref"], nets["our"]))
+        fills = sum(1 for l in open(nets["ref"][0]) if l.lstrip().startswith("fill"))
+        print(json.dumps({"tool": "chainNet -rescore", "chains": int(len(w.jobs)), "blocks": int(w.total), "t_net_fills": fills,
+                          "reference_wall_s": round(t_ref, 2), "reference_cores": 1, "ours_wall_s": round(t_ours, 2),
+                          "speedup": round(t_ref / t_ours, 2), "outputs_identical": bool(same)}))
+        if not same:
+            raise SystemExit("nets differ")
+    if "chainCleaner" in tools:  # configs[2]: chainCleaner, linearGap loose, net made like its internal system() call
+        env = dict(os.environ, PATH=refdir + ":" + os.environ["PATH"])
+        subprocess.check_call("chainNet -minScore=0 sorted.chain t.sizes q.sizes stdout /dev/null | NetFilterNonNested.perl /dev/stdin "
+                              "-minScore1 3000 > in.net", shell=True, executable="/bin/bash", cwd=d, env=env, stderr=subprocess.DEVNULL)
+        res = {}
+        for k, bindir in (("ref", refdir), ("our", ourdir)):
+            env = dict(os.environ, PATH=bindir + ":" + os.environ["PATH"])
+            cmd = [os.path.join(bindir, "chainCleaner"), "sorted.chain", "t.2bit", "q.2bit", k + ".clean.chain", k + ".clean.bed",
+                   "-net=in.net", "-linearGap=loose"]
+            t0 = time.time()
+            r = subprocess.run(cmd, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            res[k] = time.time() - t0
+            if r.returncode != 0:
+                sys.stderr.write(r.stderr.decode()[-2000:])
+                raise SystemExit("chainCleaner (%s) failed" % k)
+        same = all(filecmp.cmp(os.path.join(d, "ref.clean." + x), os.path.join(d, "our.clean." + x), shallow=False) for x in ("chain", "bed"))
+        removed = sum(1 for _ in open(os.path.join(d, "ref.clean.bed")))
+        print(json.dumps({"tool": "chainCleaner", "chains": int(len(w.jobs)), "blocks": int(w.total), "removed_suspects": removed,
+                          "reference_wall_s": round(res["ref"], 2), "reference_cores": 1, "ours_wall_s": round(res["our"], 2),
+                          "speedup": round(res["ref"] / res["our"], 2), "outputs_identical": bool(same)}))
+        if not same:
+            raise SystemExit("chainCleaner outputs differ")
 
 
 if __name__ == "__main__":
