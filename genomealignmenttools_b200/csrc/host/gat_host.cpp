@@ -822,12 +822,18 @@ void buildRecords(const ChainSet &cs, WorkList &wl)
     wl.blocks.clear();
     wl.blocks.reserve(cs.blocks.size());
     wl.chainFirstRecord.assign(cs.chains.size() + 1, 0);
+    wl.blockFirstRecord.clear();
     const uint32_t maxPiece = GAT_SPLIT_BASES;
+    bool anySplit = false;
+    for (const gat_block &b : cs.blocks)
+        if (b.size > maxPiece) { anySplit = true; break; }
+    if (anySplit) wl.blockFirstRecord.assign(cs.blocks.size() + 1, 0);
     for (size_t c = 0; c < cs.chains.size(); c++) {
         wl.chainFirstRecord[c] = wl.blocks.size();
         const ChainHead &h = cs.chains[c];
         for (uint64_t i = 0; i < h.nBlocks; i++) {
             const gat_block &b = cs.blocks[h.firstBlock + i];
+            if (anySplit) wl.blockFirstRecord[h.firstBlock + i] = wl.blocks.size();
             if (b.size <= maxPiece) { wl.blocks.push_back(b); continue; }
             // a long gapless block is cut into JOINED pieces (they score exactly like the block) so that its
             // bases spread over many warps
@@ -838,6 +844,7 @@ void buildRecords(const ChainSet &cs, WorkList &wl)
         }
     }
     wl.chainFirstRecord[cs.chains.size()] = wl.blocks.size();
+    if (anySplit) wl.blockFirstRecord[cs.blocks.size()] = wl.blocks.size();
     if (wl.blocks.size() > 0xffffffffull) fail("more than 2^32 block records in one batch");
 }
 
@@ -866,7 +873,28 @@ void addChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, Wor
             GAT_NO_CLIP_START, GAT_NO_CLIP_END, ali);
 }
 
-bool addSubChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, int subStart, int subEnd, WorkList &wl)
+bool chainAscends(const ChainSet &cs, size_t c, bool onQ)
+{
+    const ChainHead &h = cs.chains[c];
+    const gat_block *b = cs.blocks.data() + h.firstBlock;
+    for (uint64_t i = 1; i < h.nBlocks; i++) {
+        const int prevEnd = (onQ ? b[i - 1].qStart : b[i - 1].tStart) + (int)b[i - 1].size;
+        if ((onQ ? b[i].qStart : b[i].tStart) < prevEnd) return false;
+    }
+    return true;
+}
+
+uint64_t firstBlockEndingAfter(const ChainSet &cs, size_t c, int pos, bool onQ)
+{
+    const ChainHead &h = cs.chains[c];
+    const gat_block *b = cs.blocks.data() + h.firstBlock;
+    return (uint64_t)(std::partition_point(b, b + h.nBlocks, [&](const gat_block &x) {
+                          return (onQ ? x.qStart : x.tStart) + (int)x.size <= pos;
+                      }) - b);
+}
+
+bool addSubChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, int subStart, int subEnd, WorkList &wl,
+                    uint64_t firstKeptHint)
 {   // chainSubsetOnT + chainFastSubsetOnT, chain.c:471-558
     const ChainHead &h = cs.chains[c];
     if (subStart <= h.tStart && subEnd >= h.tEnd) {     // the chain itself, unclipped (:501-506)
@@ -874,7 +902,7 @@ bool addSubChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, 
         return true;
     }
     const gat_block *b = cs.blocks.data() + h.firstBlock;
-    uint64_t a = 0;
+    uint64_t a = firstKeptHint;
     while (a < h.nBlocks && b[a].tStart + (int)b[a].size <= subStart) a++;       // first block with tEnd > subStart (:479-484)
     uint64_t e = a;
     int64_t ali = 0;
@@ -884,15 +912,10 @@ bool addSubChainJob(const ChainSet &cs, size_t c, uint32_t tSeq, uint32_t qSeq, 
         e++;
     }
     if (e == a) return false;
-    // map file blocks [a, e) to device records: identical unless an earlier block of the chain was split
-    uint64_t ra = wl.chainFirstRecord[c], re;
-    if (wl.chainFirstRecord[c + 1] - wl.chainFirstRecord[c] == h.nBlocks) { ra += a; re = wl.chainFirstRecord[c] + e; }
-    else {
-        auto pieces = [&](uint64_t i) { return (uint64_t)((b[i].size + GAT_SPLIT_BASES - 1) / GAT_SPLIT_BASES) + (b[i].size == 0); };
-        for (uint64_t i = 0; i < a; i++) ra += pieces(i);
-        re = ra;
-        for (uint64_t i = a; i < e; i++) re += pieces(i);
-    }
+    // file blocks [a, e) as device records: the same indices unless a block of the batch was split
+    uint64_t ra, re;
+    if (wl.blockFirstRecord.empty()) { ra = wl.chainFirstRecord[c] + a; re = wl.chainFirstRecord[c] + e; }
+    else { ra = wl.blockFirstRecord[h.firstBlock + a]; re = wl.blockFirstRecord[h.firstBlock + e]; }
     pushJob(wl, tSeq, qSeq, h.qStrand, ra, re - ra, subStart, subEnd, ali);
     return true;
 }

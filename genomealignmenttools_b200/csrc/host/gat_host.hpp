@@ -122,6 +122,8 @@ struct WorkList {
     std::vector<gat_block> blocks;                 // device records: long blocks split into JOINED pieces
     uint64_t totalJobBlocks = 0;
     std::vector<uint64_t> chainFirstRecord;        // first device record of every chain (+ sentinel)
+    std::vector<uint64_t> blockFirstRecord;        // first device record of every file block (+ sentinel); empty when
+                                                   // no block was split (record index == block index)
     std::vector<int64_t> aliBases;                 // per job: sum of clipped sizes (scoreChain.c:182)
 };
 // Device records for all chains of a set; tSeq/qSeq come from the name->index maps.
@@ -129,7 +131,14 @@ void buildRecords(const ChainSet &cs, WorkList &wl);
 // One whole-chain job (what scoreChain scores).
 void addChainJob(const ChainSet &cs, size_t chainIx, uint32_t tSeq, uint32_t qSeq, WorkList &wl);
 // chainSubsetOnT (chain.c:471-558) as a job; returns false for kent's NULL sub-chain (no job added).
-bool addSubChainJob(const ChainSet &cs, size_t chainIx, uint32_t tSeq, uint32_t qSeq, int subStart, int subEnd, WorkList &wl);
+// firstKeptHint: callers that know the chain's blocks ascend on the target may pass the index (within the chain) of the
+// first block with tEnd > subStart, found by bisection; the default walks the chain from its head like the reference.
+bool addSubChainJob(const ChainSet &cs, size_t chainIx, uint32_t tSeq, uint32_t qSeq, int subStart, int subEnd, WorkList &wl,
+                    uint64_t firstKeptHint = 0);
+// Index (within the chain) of the first block whose end on the target (onQ: query) lies beyond `pos`, by bisection;
+// only for chains whose blocks ascend and do not overlap on that side (chainAscends).
+bool chainAscends(const ChainSet &cs, size_t chainIx, bool onQ);
+uint64_t firstBlockEndingAfter(const ChainSet &cs, size_t chainIx, int pos, bool onQ);
 // Greedy longest-processing-time split of jobs over `parts` GPUs by aligned bases.
 std::vector<std::vector<uint32_t>> shardJobs(const WorkList &wl, int parts);
 // Sub-work-list holding the given jobs (block records are shared, so only jobs are re-indexed).

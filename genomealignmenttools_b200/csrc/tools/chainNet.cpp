@@ -12,6 +12,7 @@
 #include <map>
 #include <unistd.h>
 #include "gat_host.hpp"
+#include <memory>
 
 using namespace gathost;
 
@@ -176,6 +177,18 @@ static void sortNet(int gapIx)
 
 // tFillOtherRange / qFillOtherRange, chainNet.c:389-484: refine the fill to the part of the chain
 // actually used and compute the range on the other side.
+// per chain and side: do the blocks ascend without overlap?  (-1 not looked at yet)  Then the blocks that meet a
+// range are found by bisection instead of the reference's walk over the whole list: a net has one fill per
+// aligning stretch of a chain, so walking every chain once per fill is quadratic in the long chains.
+static bool ascendingChain(const ChainSet &cs, int chain, bool onQ)
+{
+    static std::vector<signed char> known[2];
+    std::vector<signed char> &v = known[onQ];
+    if (v.size() != cs.chains.size()) v.assign(cs.chains.size(), -1);
+    if (v[chain] < 0) v[chain] = chainAscends(cs, (size_t)chain, onQ) ? 1 : 0;
+    return v[chain] == 1;
+}
+
 static void calcOtherRange(Fill &fill, const ChainSet &cs, bool isQ)
 {
     const ChainHead &h = cs.chains[fill.chain];
@@ -184,7 +197,8 @@ static void calcOtherRange(Fill &fill, const ChainSet &cs, bool isQ)
     if (isQ && isRev) { const int t = clipStart; clipStart = h.qSize - clipEnd; clipEnd = h.qSize - t; }
     int tMin = INT_MAX, tMax = -INT_MAX, qMin = INT_MAX, qMax = -INT_MAX;
     const gat_block *b = cs.blocks.data() + h.firstBlock;
-    for (uint64_t i = 0; i < h.nBlocks; i++) {
+    const uint64_t from = ascendingChain(cs, fill.chain, isQ) ? firstBlockEndingAfter(cs, (size_t)fill.chain, clipStart, isQ) : 0;
+    for (uint64_t i = from; i < h.nBlocks; i++) {
         int ts = b[i].tStart, te = ts + (int)b[i].size, qs = b[i].qStart, qe = qs + (int)b[i].size;
         if (isQ) {
             if (qe <= clipStart) continue;
@@ -228,10 +242,22 @@ struct NetWriter {
     size_t nextJob = 0;
     int depth = 0;
 
-    int baseCountSub(const ChainHead &h, int lo, int hi, bool onQ) const
+    bool ascending(int chain, bool onQ) { return ascendingChain(cs, chain, onQ); }
+
+    int baseCountSub(int chain, int lo, int hi, bool onQ)
     {   // chainBaseCountSubT / chainBaseCountSubQ, :773-793
+        const ChainHead &h = cs.chains[chain];
         int total = 0;
         const gat_block *b = cs.blocks.data() + h.firstBlock;
+        if (ascending(chain, onQ)) {
+            for (uint64_t i = firstBlockEndingAfter(cs, (size_t)chain, lo, onQ); i < h.nBlocks; i++) {
+                const int s = onQ ? b[i].qStart : b[i].tStart, e = s + (int)b[i].size;
+                if (s >= hi) break;
+                const int x = std::min(e, hi) - std::max(s, lo);
+                if (x > 0) total += x;
+            }
+            return total;
+        }
         for (uint64_t i = 0; i < h.nBlocks; i++) {
             const int s = onQ ? b[i].qStart : b[i].tStart, e = s + (int)b[i].size;
             const int x = std::min(e, hi) - std::max(s, lo);
@@ -248,16 +274,17 @@ struct NetWriter {
         if (isQ) {
             if (h.qStrand == '-') { const int t = start; start = h.qSize - end; end = h.qSize - t; }
             if (start <= h.qStart && end >= h.qEnd) { subScore = h.score; subSize = fullSize; }
-            else { subSize = baseCountSub(h, start, end, true); subScore = h.score * subSize / fullSize; }
+            else { subSize = baseCountSub(fill.chain, start, end, true); subScore = h.score * subSize / fullSize; }
             return;
         }
         if (start <= h.tStart && end >= h.tEnd) { subScore = h.score; subSize = fullSize; return; }
-        subSize = baseCountSub(h, start, end, false);
+        subSize = baseCountSub(fill.chain, start, end, false);
         if (!rescore) { subScore = h.score * subSize / fullSize; return; }
         if (f == nullptr) {                         // collecting pass: queue the clipped job
             subScore = 1;
             if (subSize >= minFill) {
-                if (!addSubChainJob(cs, fill.chain, (*chainT)[fill.chain], (*chainQ)[fill.chain], start, end, *wl))
+                const uint64_t hint = ascending(fill.chain, false) ? firstBlockEndingAfter(cs, (size_t)fill.chain, start, false) : 0;
+                if (!addSubChainJob(cs, fill.chain, (*chainT)[fill.chain], (*chainQ)[fill.chain], start, end, *wl, hint))
                     errAbort("fill %d-%d of chain %d holds no aligned block", start, end, h.id);
             }
         } else {
@@ -366,6 +393,9 @@ static int toolMain(int argc, char **argv)
 
     const char *chainFile = argv[1], *tSizes = argv[2], *qSizes = argv[3], *tNet = argv[4], *qNet = argv[5];
     ChainSet cs;
+    phaseDone("start");
+    std::unique_ptr<GpuStarter> gpuStarter;             // -rescore: the CUDA contexts come up while the nets are built
+    if (rescore) gpuStarter.reset(new GpuStarter(opt.intVal("gpus", 1)));
     readChains(chainFile, cs);
     FILE *tNetFile = strcmp(tNet, "stdout") == 0 ? stdout : fopen(tNet, "w");
     if (!tNetFile) errAbort("mustOpen: Can't open %s to write: %s", tNet, strerror(errno));
@@ -378,6 +408,7 @@ static int toolMain(int argc, char **argv)
     readSizes(tSizes, tChroms, tIndex);
     verbose(1, "Got %d chroms in %s, %d in %s\n", (int)tChroms.size(), tSizes, (int)qChroms.size(), qSizes);
 
+    phaseDone("chains read");
     // build the nets, best chain first (chainNet.c:941-975)
     double lastScore = -1;
     size_t consumed = cs.chains.size();
@@ -412,12 +443,14 @@ static int toolMain(int argc, char **argv)
             fprintf(qNetFile, "%s\n", cs.metaLines[i].c_str());
         }
 
+    phaseDone("chains added to the nets");
     verbose(1, "Finishing nets\n");
     for (Chrom &c : qChroms)
         if (!gaps[c.root].fills.empty()) { sortNet(c.root); calcOtherRanges(c.root, cs, true); }
     for (Chrom &c : tChroms)
         if (!gaps[c.root].fills.empty()) { sortNet(c.root); calcOtherRanges(c.root, cs, false); }
 
+    phaseDone("nets sorted, other ranges");
     std::vector<int> chainBases(cs.chains.size(), 0);       // chainBaseCount, :762-771
     for (size_t c = 0; c < cs.chains.size(); c++)
         for (uint64_t i = 0; i < cs.chains[c].nBlocks; i++) chainBases[c] += (int)cs.blocks[cs.chains[c].firstBlock + i].size;
@@ -446,15 +479,18 @@ static int toolMain(int argc, char **argv)
         NetWriter collect{cs, chainBases, false};
         collect.wl = &wl; collect.chainT = &chainT; collect.chainQ = &chainQ;
         collect.outSide(tChroms);
+        phaseDone("partial fills collected");
         verbose(2, "rescoring %d partial fills (%llu job-blocks) on the GPU\n", (int)wl.jobs.size(), (unsigned long long)wl.totalJobBlocks);
         if (!wl.jobs.empty()) {
-            MultiGpu gpus(opt.intVal("gpus", 1));
+            MultiGpu &gpus = gpuStarter->get();
             for (gat_ctx *ctx : gpus.ctx) {
                 uploadGenome(ctx, GAT_TARGET, tbT, useT);
                 uploadGenome(ctx, GAT_QUERY, tbQ, useQ);
                 setScoring(ctx, scheme, gapCalc);
             }
+            phaseDone("contexts + genomes");
             gpus.score(wl, global, local);
+            phaseDone("fills rescored on the GPU");
         }
     }
 
@@ -467,6 +503,7 @@ static int toolMain(int argc, char **argv)
     qw.outSide(qChroms);
     if (tNetFile != stdout) fclose(tNetFile);
     if (qNetFile != stdout) fclose(qNetFile);
+    phaseDone("nets written");
     return 0;
 }
 

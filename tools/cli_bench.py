@@ -101,6 +101,8 @@ def main():
         nets = {k: [os.path.join(d, "%s.%s.net" % (k, x)) for x in "tq"] for k in ("ref", "our")}
         t_ref = timed([os.path.join(refdir, "chainNet")] + common + nets["ref"])
         t_ours = min(timed([os.path.join(ourdir, "chainNet")] + common + nets["our"]) for _ in range(2))
+        sys.stderr.write(subprocess.run([os.path.join(ourdir, "chainNet")] + common + nets["our"], stderr=subprocess.PIPE,
+                                        env=dict(os.environ, GAT_TOOL_TIMING="1")).stderr.decode())
         same = all(filecmp.cmp(a, b, shallow=False) for a, b in zip(nets["ref"], nets["our"]))
         fills = sum(1 for l in open(nets["ref"][0]) if l.lstrip().startswith("fill"))
         print(json.dumps({"tool": "chainNet -rescore", "chains": int(len(w.jobs)), "blocks": int(w.total), "t_net_fills": fills,
