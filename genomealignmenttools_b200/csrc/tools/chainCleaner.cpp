@@ -344,7 +344,7 @@ struct Request { int chainId, subStart, subEnd; };
 
 class Scorer {
 public:
-    Scorer(int nGpus, const TwoBitFile &tbT, const TwoBitFile &tbQ, const ScoreScheme &ss, const GapCalc &gc) : gpus(nGpus)
+    Scorer(GpuStarter &starter, const TwoBitFile &tbT, const TwoBitFile &tbQ, const ScoreScheme &ss, const GapCalc &gc) : gpus(starter.get())
     {
         // like loadTandQSeqs (chainCleaner.c:463-480) only the sequences of chains of interest go to the GPU
         std::vector<int> useT, useQ, mapT(tbT.seqs().size(), -1), mapQ(tbQ.seqs().size(), -1);
@@ -410,7 +410,7 @@ public:
     }
     size_t gpuCalls = 0, gpuJobs = 0;
 private:
-    MultiGpu gpus;
+    MultiGpu &gpus;
 };
 
 // The four sub-chains of one tested suspect (chainCleaner.c:1214-1217).  Their scores stay valid until blocks are
@@ -704,6 +704,8 @@ static int toolMain(int argc, char **argv)
     if (access(tNibDir, F_OK) != 0) errAbort("ERROR: target 2bit file or nib directory %s does not exist\n", tNibDir);
     if (access(qNibDir, F_OK) != 0) errAbort("ERROR: query 2bit file or nib directory %s does not exist\n", qNibDir);
 
+    GpuStarter gpuStarter(opt.intVal("gpus", 1));      // the CUDA contexts come up while nets and chains are parsed
+
     // 0. net the chains ourselves if no net was given (chainCleaner.c:1639-1670)
     std::string tmpNet;
     if (!inNetFile) {
@@ -791,7 +793,7 @@ static int toolMain(int argc, char **argv)
     verbose(1, "3. reading target and query DNA sequences for breaking and broken chains ...\n");
     TwoBitFile tbT(tNibDir), tbQ(qNibDir);
     std::unique_ptr<Scorer> scorer;
-    if (!live.empty()) scorer.reset(new Scorer(opt.intVal("gpus", 1), tbT, tbQ, scheme, gapCalc));
+    if (!live.empty()) scorer.reset(new Scorer(gpuStarter, tbT, tbQ, scheme, gapCalc));
     verbose(1, "DONE\n\n");
 
     // 4. the suspect loop
