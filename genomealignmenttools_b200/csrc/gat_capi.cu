@@ -49,6 +49,7 @@ struct gat_ctx {
     // scoring
     bool scoringSet = false, sym = false;
     int coef[16];
+    int matrix[16];                     // as given, [q][t]: the crossover kernel looks entries up
     GapView gap;
     int *gapSmall = nullptr, *gapLongPos = nullptr, *gapDense = nullptr;
     double *gapLongVal = nullptr;
@@ -304,6 +305,8 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
     }
     ctx->sym = symmetricCoefs(s->matrix, ctx->coef);
     if (!ctx->sym) moebiusCoefs(s->matrix, ctx->coef);
+    for (int q = 0; q < 4; q++)
+        for (int t = 0; t < 4; t++) ctx->matrix[q * 4 + t] = s->matrix[q][t];
     const int S = s->smallSize, L = s->longCount;
     std::vector<int> small(3 * (size_t)S);
     std::vector<double> longVal(3 * (size_t)L);
@@ -586,6 +589,42 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
         ctx->stats.h2d_bytes = nJobs * sizeof(gat_job) + nBlocks * sizeof(gat_block);
         ctx->stats.d2h_bytes = 2 * nJobs * sizeof(long long);
     }
+    return rc;
+}
+
+extern "C" int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPairs, int32_t *pos, int32_t *adjust)
+{
+    if (!ctx) return fail(GAT_EINVAL, "gat_crossover: NULL ctx");
+    if (nPairs && (!pairs || !pos || !adjust)) return fail(GAT_EINVAL, "gat_crossover: NULL array");
+    if (!ctx->genome[0].loaded || !ctx->genome[1].loaded) return fail(GAT_ESTATE, "gat_crossover: load both genomes first");
+    if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_crossover: call gat_set_scoring first");
+    if (nPairs == 0) return GAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    gat_xpair *dPairs = nullptr;
+    int *dOut = nullptr;
+    CU(cudaMalloc(&dPairs, nPairs * sizeof(gat_xpair)));
+    if (cudaMalloc(&dOut, 2 * nPairs * sizeof(int)) != cudaSuccess) { cudaFree(dPairs); return fail(GAT_ENOMEM, "gat_crossover: out of device memory"); }
+    XoverParams P;
+    P.pairs = dPairs; P.nPairs = nPairs;
+    P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
+    memcpy(P.matrix, ctx->matrix, sizeof P.matrix);
+    P.pos = dOut; P.adjust = dOut + nPairs; P.err = ctx->err;
+    int rc = GAT_OK, err = 0;
+    cudaError_t e = cudaMemcpyAsync(dPairs, pairs, nPairs * sizeof(gat_xpair), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        crossoverKernel<<<(unsigned)((nPairs + 127) / 128), 128, 0, st>>>(P);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pos, P.pos, nPairs * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(adjust, P.adjust, nPairs * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(GAT_ECUDA, "gat_crossover failed: %s", cudaGetErrorString(e));
+    if (rc == GAT_OK) rc = readDeviceError(ctx, &err);
+    cudaStreamSynchronize(st);
+    cudaFree(dPairs); cudaFree(dOut);
+    if (rc == GAT_OK && err)
+        rc = fail(GAT_EWORKLIST, "crossover pairs rejected by the device:%s%s", (err & ERR_SEQ) ? " sequence index out of range;" : "",
+                  (err & ERR_COORD) ? " overlap outside its sequence;" : "");
     return rc;
 }
 

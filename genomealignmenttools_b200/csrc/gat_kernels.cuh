@@ -998,4 +998,64 @@ __global__ void revCompKernel(const uint32_t *__restrict__ seqSize, const long l
     if (rn) atomicOr(&nwin[(n >> 3) >> 5], 1u << ((n >> 3) & 31));
 }
 
+// ------------------------------------------------------------------ crossover of overlapping blocks
+// cBlockFindCrossover (kent/src/lib/chainConnect.c:61-105), one thread per pair.  With L[i], R[i] the scores of base i
+// of the overlap in the left / right block, the reference starts from sum(R), adds L[i] - R[i] base by base and keeps
+// the first strictly better position: pos = first argmax of the prefix sums P (0 if none is positive) and
+// retScoreAdjustment = sum(R) + sum(L) - (sum(R) + max(0, max P)) = sum(L) - max(0, max P).
+struct XoverParams {
+    const gat_xpair *pairs;
+    unsigned long long nPairs;
+    GenomeView t, q;            // q.seqBase holds forward images then reverse-complement images
+    int matrix[16];             // [q][t], kent base codes
+    int *pos, *adjust;
+    int *err;
+};
+
+__device__ __forceinline__ void xoverWindow(const GenomeView &g, long long base, uint32_t &hi, uint32_t &lo, uint32_t &n)
+{   // 32 bases starting at padded coordinate `base`
+    const uint32_t w = (uint32_t)(base >> 5), sh = (uint32_t)(base & 31);
+    loadWindow(g.planes, w, sh, hi, lo);
+    n = loadNWindow(g.nplane, w, sh);
+}
+
+__global__ void crossoverKernel(const __grid_constant__ XoverParams P)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nPairs) return;
+    const gat_xpair p = P.pairs[i];
+    const uint32_t qSeq = p.qSeq & 0x7fffffffu;
+    if (p.tSeq >= P.t.nSeq || qSeq >= P.q.nSeq) { atomicOr(P.err, ERR_SEQ); return; }
+    const long long tSize = P.t.seqSize[p.tSeq], qSize = P.q.seqSize[qSeq], ov = p.overlap;
+    if (ov < 0 || p.leftTEnd - ov < 0 || p.leftQEnd - ov < 0 || p.leftTEnd > tSize || p.leftQEnd > qSize ||
+        p.rightTStart < 0 || p.rightQStart < 0 || p.rightTStart + ov > tSize || p.rightQStart + ov > qSize) {
+        atomicOr(P.err, ERR_COORD);
+        return;
+    }
+    const long long tBase = P.t.seqBase[p.tSeq], qBase = P.q.seqBase[(p.qSeq >> 31) ? P.q.nSeq + qSeq : qSeq];
+    const long long lt = tBase + p.leftTEnd - ov, lq = qBase + p.leftQEnd - ov, rt = tBase + p.rightTStart, rq = qBase + p.rightQStart;
+    long long sumL = 0, prefix = 0, best = 0;
+    int bestPos = 0;
+    for (long long off = 0; off < ov; off += 32) {
+        uint32_t lt1, lt0, ltn, lq1, lq0, lqn, rt1, rt0, rtn, rq1, rq0, rqn;
+        xoverWindow(P.t, lt + off, lt1, lt0, ltn);
+        xoverWindow(P.q, lq + off, lq1, lq0, lqn);
+        xoverWindow(P.t, rt + off, rt1, rt0, rtn);
+        xoverWindow(P.q, rq + off, rq1, rq0, rqn);
+        const uint32_t ln = ltn | lqn, rn = rtn | rqn;        // N on either side scores 0 (axt.c:431-454)
+        const int nb = ov - off < 32 ? (int)(ov - off) : 32;
+        for (int b = 0; b < nb; b++) {
+            const int lcode = (int)((((lq1 >> b) & 1u) << 3) | (((lq0 >> b) & 1u) << 2) | (((lt1 >> b) & 1u) << 1) | ((lt0 >> b) & 1u));
+            const int rcode = (int)((((rq1 >> b) & 1u) << 3) | (((rq0 >> b) & 1u) << 2) | (((rt1 >> b) & 1u) << 1) | ((rt0 >> b) & 1u));
+            const int L = ((ln >> b) & 1u) ? 0 : P.matrix[lcode];
+            const int R = ((rn >> b) & 1u) ? 0 : P.matrix[rcode];
+            sumL += L;
+            prefix += L - R;
+            if (prefix > best) { best = prefix; bestPos = (int)off + b + 1; }
+        }
+    }
+    P.pos[i] = bestPos;
+    P.adjust[i] = (int)(sumL - best);
+}
+
 }  // namespace gat

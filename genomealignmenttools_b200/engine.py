@@ -85,6 +85,15 @@ class ChainScorer:
     def __exit__(self, *a):
         self.close()
 
+    def crossover(self, pairs):
+        """cBlockFindCrossover (kent chainConnect.c:61-105) for a batch of overlapping block pairs (XPAIR_DTYPE):
+        returns (pos, adjust) int32 arrays."""
+        from .records import XPAIR_DTYPE
+        pairs = np.ascontiguousarray(pairs, dtype=XPAIR_DTYPE)
+        pos = np.zeros(len(pairs), dtype=np.int32); adj = np.zeros(len(pairs), dtype=np.int32)
+        self._check(self.lib.gat_crossover(self.ctx, _ptr(pairs), len(pairs), _ptr(pos), _ptr(adj)))
+        return pos, adj
+
     def max_record_bases(self):
         """Longest record (gat_block.size) the device accepts under the current scoring parameters."""
         return int(self.lib.gat_max_record_bases(self.ctx))

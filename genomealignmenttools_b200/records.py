@@ -75,3 +75,7 @@ def split_long_blocks(jobs, total_job_blocks, blocks, max_bases=SPLIT_BASES):
     new_jobs["firstBlock"] = first[jobs["firstBlock"].astype(np.int64)]
     new_jobs["blockPtr"] = new_jobs["firstBlock"]
     return new_jobs, int(first[-1]), out
+
+# gat_xpair (include/gat.h): one pair of overlapping adjacent blocks for gat_crossover
+XPAIR_DTYPE = np.dtype([("tSeq", "<u4"), ("qSeq", "<u4"), ("leftTEnd", "<i4"), ("leftQEnd", "<i4"),
+                        ("rightTStart", "<i4"), ("rightQStart", "<i4"), ("overlap", "<i4")])

@@ -147,6 +147,24 @@ int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl);           /* asynchronous 
 int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local);
 void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl);
 
+/* Crossover points of overlapping adjacent blocks, in one batch: what kent's chainRemovePartialOverlaps asks of
+ *     void cBlockFindCrossover(struct cBlock *left, struct cBlock *right, struct dnaSeq *qSeq, struct dnaSeq *tSeq,
+ *                              int overlap, int matrix[256][256], int *retPos, int *retScoreAdjustment)
+ *                                                   kent/src/inc/chainConnect.h, kent/src/lib/chainConnect.c:61-105
+ * once per overlapping pair (kent/src/lib/chainConnect.c:284-296; axtChain's last step before it rescoring).
+ * The left block ends at (leftTEnd, leftQEnd), the right block starts at (rightTStart, rightQStart); their last / first
+ * `overlap` bases are compared base by base.  pos[i] = offset from the start of the overlap at which the right block
+ * takes over (0..overlap, the first best one), adjust[i] = retScoreAdjustment.  Query coordinates are the chain's own
+ * (reverse-complement space on '-').  Uses the matrix of gat_set_scoring; gap tables play no part. */
+typedef struct gat_xpair {
+    uint32_t tSeq;        /* target sequence index */
+    uint32_t qSeq;        /* query sequence index | GAT_QSEQ_MINUS */
+    int32_t leftTEnd, leftQEnd;
+    int32_t rightTStart, rightQStart;
+    int32_t overlap;      /* >= 0 */
+} gat_xpair;
+int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPairs, int32_t *pos, int32_t *adjust);
+
 int gat_synchronize(gat_ctx *ctx);
 int gat_get_stats(gat_ctx *ctx, gat_stats *out);
 /* When on, gat_worklist_run/gat_score bracket each kernel with CUDA events (filled into gat_stats). */

@@ -502,6 +502,25 @@ double orc_score_block(const orc_scoring *s, const char *q, const char *t, int s
     return total;
 }
 
+void orc_find_crossover(const orc_scoring *s, const char *q, const char *t, int leftTEnd, int leftQEnd,
+                        int rightTStart, int rightQStart, int overlap, int *pos, int *adjust)
+/* chainConnect.c:80-104: start from "all of the overlap goes to the right block", move the switch point base by
+ * base (the left block gains a base, the right one loses it) and keep the first best position. */
+{
+    const char *rq = q + rightQStart, *lq = q + leftQEnd - overlap;
+    const char *rt = t + rightTStart, *lt = t + leftTEnd - overlap;
+    double rScore = orc_score_block(s, rq, rt, overlap), lScore = orc_score_block(s, lq, lt, overlap);
+    double score = rScore, best = rScore;
+    int bestPos = 0;
+    for (int i = 0; i < overlap; i++) {
+        score += s->matrix[(unsigned char)lq[i]][(unsigned char)lt[i]];
+        score -= s->matrix[(unsigned char)rq[i]][(unsigned char)rt[i]];
+        if (score > best) { best = score; bestPos = i + 1; }
+    }
+    *pos = bestPos;
+    *adjust = (int)(rScore + lScore - best);
+}
+
 int orc_score_jobs(const orc_scoring *s, orc_genome *tg, orc_genome *qg,
                    const orc_job *jobs, int64_t nJobs, int64_t totalJobBlocks,
                    const orc_block *blocks, int64_t nBlocks,

@@ -62,6 +62,13 @@ int orc_score_jobs(const orc_scoring *s, orc_genome *tg, orc_genome *qg,
                    const orc_block *blocks, int64_t nBlocks,
                    int64_t *global, int64_t *local, int64_t *aliBases);
 
+/* Crossover point of two overlapping blocks (cBlockFindCrossover, chainConnect.c:61-105): left ends at
+ * (leftTEnd, leftQEnd), right starts at (rightTStart, rightQStart), the last / first `overlap` bases of the two
+ * cover the same stretch.  pos = offset from the start of the overlap at which to switch to the right block,
+ * adjust = what the pair loses against the sum of both overlaps.  q/t: 1 char/base sequences (query in chain strand). */
+void orc_find_crossover(const orc_scoring *s, const char *q, const char *t, int leftTEnd, int leftQEnd,
+                        int rightTStart, int rightQStart, int overlap, int *pos, int *adjust);
+
 /* ---- .chain (chain.c:256-346) */
 orc_chainset *orc_chains_read(const char *path);
 void orc_chains_free(orc_chainset *cs);

@@ -129,3 +129,26 @@ struct dnaSeq *seq = getSeqFromHash((char *)name, strand, isTarget ? tSeqHash : 
 *retDna = seq->dna;
 return seq->size;
 }
+
+void ref_crossover(const char *tName, const char *qName, char qStrand, int n,
+	const int *leftTEnd, const int *leftQEnd, const int *rightTStart, const int *rightQStart,
+	const int *overlap, int *pos, int *adjust)
+/* cBlockFindCrossover (kent/src/lib/chainConnect.c:61-105) on blocks that carry just the fields it reads. */
+{
+int i;
+struct dnaSeq *qSeq, *tSeq;
+loadSeq(t2bit, TRUE, (char *)tName, tSeqHash);
+loadSeq(q2bit, FALSE, (char *)qName, qSeqHash);
+qSeq = getSeqFromHash((char *)qName, qStrand, qSeqHash);
+tSeq = getSeqFromHash((char *)tName, '+', tSeqHash);
+for (i=0; i<n; ++i)
+    {
+    struct cBlock left, right;
+    ZeroVar(&left); ZeroVar(&right);
+    left.tEnd = leftTEnd[i]; left.qEnd = leftQEnd[i];
+    left.tStart = left.tEnd - overlap[i]; left.qStart = left.qEnd - overlap[i];
+    right.tStart = rightTStart[i]; right.qStart = rightQStart[i];
+    right.tEnd = right.tStart + overlap[i]; right.qEnd = right.qStart + overlap[i];
+    cBlockFindCrossover(&left, &right, qSeq, tSeq, overlap[i], scoreScheme->matrix, &pos[i], &adjust[i]);
+    }
+}

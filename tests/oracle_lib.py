@@ -63,6 +63,19 @@ class Oracle:
             raise RuntimeError(self.err())
         return g, l, a
 
+    def crossover(self, scoring, tg, qg, t_ix, q_ix, strand, pairs):
+        """pairs: rows of (leftTEnd, leftQEnd, rightTStart, rightQStart, overlap) on one sequence pair."""
+        self.lib.orc_genome_dna.restype = ctypes.c_void_p
+        t = self.lib.orc_genome_dna(tg, int(t_ix), b"+")
+        q = self.lib.orc_genome_dna(qg, int(q_ix), strand.encode())
+        self.lib.orc_find_crossover.argtypes = [_vp, _vp, _vp] + [_i32] * 5 + [_vp, _vp]
+        pos, adj = [], []
+        for lt, lq, rt, rq, ov in pairs:
+            a, b = ctypes.c_int(), ctypes.c_int()
+            self.lib.orc_find_crossover(scoring, q, t, int(lt), int(lq), int(rt), int(rq), int(ov), ctypes.byref(a), ctypes.byref(b))
+            pos.append(a.value); adj.append(b.value)
+        return np.array(pos, dtype=np.int32), np.array(adj, dtype=np.int32)
+
     def chains(self, path):
         cs = self.lib.orc_chains_read(str(path).encode())
         if not cs:
@@ -136,6 +149,15 @@ class KentRef:
         g = np.zeros(n); l = np.zeros(n); a = np.zeros(n, dtype=np.int32)
         self.lib.ref_score_all(g.ctypes.data, l.ctypes.data, a.ctypes.data)
         return g.astype(np.int64), l.astype(np.int64), a.astype(np.int64)
+
+    def crossover(self, t_name, q_name, strand, pairs):
+        cols = [np.ascontiguousarray([p[k] for p in pairs], dtype=np.int32) for k in range(5)]
+        n = len(pairs)
+        pos = np.zeros(n, dtype=np.int32); adj = np.zeros(n, dtype=np.int32)
+        self.lib.ref_crossover.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char, _i32] + [_vp] * 7
+        self.lib.ref_crossover(t_name.encode(), q_name.encode(), strand.encode(), n, *[c.ctypes.data for c in cols],
+                               pos.ctypes.data, adj.ctypes.data)
+        return pos, adj
 
     def score_sub(self, ix, s, e):
         ix = np.ascontiguousarray(ix, dtype=np.int32); s = np.ascontiguousarray(s, dtype=np.int32)

@@ -270,6 +270,47 @@ def test_record_length_limit_follows_the_matrix(oracle, tmp_path):
             sc.set_scoring(too_big)
 
 
+def test_crossover_matches_oracle(oracle, tmp_path):
+    """gat_crossover (cBlockFindCrossover, kent chainConnect.c:61-105) against the oracle: both strands, N runs, two
+    matrices, overlaps of 0..150 bases at arbitrary offsets, sequence ends; out-of-range pairs are rejected."""
+    from genomealignmenttools_b200.records import XPAIR_DTYPE
+    from test_oracle import crossover_cases
+    w, tn, qn = small_world(seed=21, n_blocks=3000)
+    paths = helpers.write_case(w, tn, qn, tmp_path)
+    tg, qg = oracle.genome(paths["t"]), oracle.genome(paths["q"])
+    rng = np.random.default_rng(8)
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q)
+        for matrix in (None, "synth_small/asym.q"):
+            golden = os.path.join(os.path.dirname(__file__), "golden")
+            sc.set_scoring(scoring_of(golden, matrix, "loose"))
+            s = oracle.scoring(os.path.join(golden, matrix) if matrix else None, "loose")
+            for ti, qi, strand in ((0, 0, "+"), (1, 1, "-"), (0, 1, "-"), (1, 0, "+")):
+                tsz, qsz = int(w.t.sizes[ti]), int(w.q.sizes[qi])
+                cases = crossover_cases(rng, tsz, qsz, 600)
+                cases += [(tsz, qsz, 0, 0, 64), (64, 64, tsz - 64, qsz - 64, 64), (1, 1, 0, 0, 1), (10, 10, 5, 5, 0)]
+                # overlaps along planted homology: block starts of real chains, shifted against themselves
+                for j in np.nonzero((w.jobs["tSeq"] == ti) & ((w.jobs["qSeq"] & 0x7FFFFFFF) == qi) &
+                                    ((w.jobs["qSeq"] >> 31) == (1 if strand == "-" else 0)))[0][:150]:
+                    b = w.blocks[int(w.jobs[j]["firstBlock"])]
+                    ov = int(min(b["size"], 90))
+                    if ov >= 4:
+                        cases.append((int(b["tStart"]) + ov, int(b["qStart"]) + ov, int(b["tStart"]) + ov // 3, int(b["qStart"]) + ov // 3, ov - ov // 3))
+                pairs = np.zeros(len(cases), dtype=XPAIR_DTYPE)
+                pairs["tSeq"] = ti; pairs["qSeq"] = qi | (QSEQ_MINUS if strand == "-" else 0)
+                for k, name in enumerate(("leftTEnd", "leftQEnd", "rightTStart", "rightQStart", "overlap")):
+                    pairs[name] = [c[k] for c in cases]
+                pos, adj = sc.crossover(pairs)
+                opos, oadj = oracle.crossover(s, tg, qg, ti, qi, strand, cases)
+                assert np.array_equal(pos, opos) and np.array_equal(adj, oadj)
+                assert (pos > 0).sum() > 10
+        bad = np.zeros(1, dtype=XPAIR_DTYPE); bad["leftTEnd"] = 5; bad["leftQEnd"] = 5; bad["overlap"] = 9
+        with pytest.raises(GatError):
+            sc.crossover(bad)
+        pos, adj = sc.crossover(np.zeros(0, dtype=XPAIR_DTYPE))
+        assert len(pos) == 0
+
+
 def test_resident_worklist_matches_one_shot():
     w, _, _ = small_world(seed=12, n_blocks=9000)
     with ChainScorer(0) as sc:

@@ -171,3 +171,40 @@ def test_oracle_vs_live_reference_random(oracle, kentref, tmp_path):
                                     jobs, ptr, w.blocks)
         live = rz == 0
         assert np.array_equal(g[live], rg[live]) and np.array_equal(l[live], rl[live]) and np.array_equal(a[live], ra[live])
+
+
+def crossover_cases(rng, t_size, q_size, n, max_overlap=150):
+    """Random (leftTEnd, leftQEnd, rightTStart, rightQStart, overlap) with every overlap inside both sequences."""
+    out = []
+    for _ in range(n):
+        ov = int(rng.integers(0, max_overlap))
+        lt = int(rng.integers(ov, t_size + 1)); lq = int(rng.integers(ov, q_size + 1))
+        rt = int(rng.integers(0, t_size - ov + 1)); rq = int(rng.integers(0, q_size - ov + 1))
+        out.append((lt, lq, rt, rq, ov))
+    return out
+
+
+def test_crossover_against_live_reference(oracle, kentref, tmp_path):
+    """orc_find_crossover vs the unmodified cBlockFindCrossover (kent chainConnect.c:61-105), both strands, with N."""
+    if kentref is None:
+        pytest.skip("oracle/_ref not built here")
+    from genomealignmenttools_b200 import synth
+    import make_golden_helpers as helpers
+    rng = np.random.default_rng(123)
+    w = synth.make_workload(["a", "b"], [30011, 8002], ["x", "y"], [25003, 9001], 800, seed=77, telomere_n=300, n_fraction=0.05,
+                            max_chain_blocks=100)
+    paths = helpers.write_case(w, ["a", "b"], ["x", "y"], tmp_path)
+    for matrix in (None, os.path.join(os.path.dirname(__file__), "golden/synth_small/asym.q")):
+        kentref.set_scoring(matrix, "loose")
+        kentref.open(paths["t"], paths["q"], paths["chain"])
+        s = oracle.scoring(matrix, "loose")
+        tg, qg = oracle.genome(paths["t"]), oracle.genome(paths["q"])
+        for (ti, tn, tsz), (qi, qn, qsz), strand in (((0, "a", 30011), (0, "x", 25003), "+"), ((1, "b", 8002), (1, "y", 9001), "-"),
+                                                     ((0, "a", 30011), (1, "y", 9001), "-")):
+            cases = crossover_cases(rng, tsz, qsz, 400)
+            # overlaps of homologous stretches (planted along chain blocks) are where a crossover is not trivial
+            cases += [(lt, lq, lt - ov // 2, lq - ov // 2, ov) for lt, lq, _, _, ov in cases[:200] if lt - ov // 2 + ov <= tsz and lq - ov // 2 + ov <= qsz]
+            rp, ra = kentref.crossover(tn, qn, strand, cases)
+            op, oa = oracle.crossover(s, tg, qg, ti, qi, strand, cases)
+            assert np.array_equal(op, rp) and np.array_equal(oa, ra)
+            assert (rp > 0).sum() > 20
