@@ -37,18 +37,29 @@ def log(*a):
 
 
 # --------------------------------------------------------------------------- workload
-def build_workload(blocks_per_gpu, world=1, plant=True, mean_log_len=3.6, max_len=30000):
+def build_workload(blocks_per_gpu, world=1, plant=True, mean_log_len=3.6, max_len=30000, rank=0, exchange=None):
     """The whole job for `world` GPUs: world x blocks_per_gpu job-blocks (weak scaling), generated in
-    `world` seeded parts so that N=1 is exactly part 0.  Every rank builds the identical set."""
+    `world` seeded parts so that N=1 is exactly part 0.  Every rank ends up with the identical set: either
+    it generates all parts itself, or (exchange given) only part `rank` and the ranks swap parts -- the chain
+    generator is the slow step of the set-up (about 10 s and 3 GB per part)."""
     from genomealignmenttools_b200 import synth
     tn, ts = synth.read_chrom_sizes(os.path.join(GOLDEN, "example", "hg38.chrom.sizes"))
     qn, qs = synth.read_chrom_sizes(os.path.join(GOLDEN, "example", "mm10.chrom.sizes"))
     t0 = time.time()
     t = synth.random_genome(tn, ts, 0x5EED0001, telomere_n=10000)
     q = synth.random_genome(qn, qs, 0x5EED0002, telomere_n=10000)
-    job_parts, block_parts, total = [], [], 0
-    for part in range(world):
+
+    def chains_of(part):
         jobs, n, blocks = synth.make_chains(ts, qs, blocks_per_gpu, seed=0x5EED0050 + part, mean_log_len=mean_log_len, max_len=max_len)
+        return jobs, blocks
+
+    if exchange is not None and world > 1:
+        parts = exchange(*chains_of(rank))
+    else:
+        parts = [chains_of(part) for part in range(world)]
+    job_parts, block_parts, total = [], [], 0
+    for part, (jobs, blocks) in enumerate(parts):
+        n = len(blocks)
         if plant:
             synth.plant_homology(t, q, jobs, n, blocks, 0.30, 0x5EED0060 + part)
         synth.sprinkle_n_runs(t, "t", jobs, blocks, 0.0005, 0x5EED0070 + part)
@@ -295,7 +306,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    w, _ = shard_workload(build_workload(args.blocks, world, mean_log_len=args.mean_log_len, max_len=args.max_len), rank, world)
+    def exchange(jobs, blocks):
+        """Set-up only: every rank generated one part of the chain set; swap them (NCCL all_gather of raw bytes)."""
+        cols = []
+        for arr, dtype in ((jobs, JOB_DTYPE), (blocks, BLOCK_DTYPE)):
+            raw = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).cuda()
+            n = torch.tensor([raw.numel()], dtype=torch.int64, device="cuda")
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, n)
+            sizes = [int(x.item()) for x in sizes]
+            buf = torch.zeros(max(sizes), dtype=torch.uint8, device="cuda")
+            buf[:raw.numel()] = raw
+            got = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(got, buf)
+            cols.append([g[:k].cpu().numpy().view(dtype).copy() for g, k in zip(got, sizes)])
+            del raw, buf, got
+        torch.cuda.empty_cache()
+        return list(zip(*cols))
+
+    w, _ = shard_workload(build_workload(args.blocks, world, mean_log_len=args.mean_log_len, max_len=args.max_len, rank=rank,
+                                         exchange=exchange if world > 1 else None), rank, world)
     if args.split:
         from genomealignmenttools_b200.records import split_long_blocks
         bp = w.aligned_bp
