@@ -248,6 +248,28 @@ def cpu_reference(w, steps, warmup, max_aligned_bp, gpu_scores=None):
             "ms_per_step": sec * 1e3, "aligned_bp": bp}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned work-list buffers of the e2e leg are
+    first-touched next to the GPU (8 ranks copying 50 GB/s each across sockets do not scale).  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(gpu_index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -298,6 +320,7 @@ def main():
     from genomealignmenttools_b200.records import JOB_DTYPE, BLOCK_DTYPE
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -345,7 +368,7 @@ def main():
     sc.load_genome("t", w.t)
     sc.load_genome("q", w.q)
     sc.set_scoring(Scoring(None, "medium"))
-    log("[rank %d] genomes resident in HBM after %.1f s" % (rank, time.time() - t0))
+    log("[rank %d] genomes resident in HBM after %.1f s (NUMA node %s)" % (rank, time.time() - t0, numa))
 
     # ---- device-resident timing (value)
     wl = sc.upload(w.jobs, w.total, w.blocks)
