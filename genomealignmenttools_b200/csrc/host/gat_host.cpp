@@ -9,11 +9,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
+#include <map>
 #include <memory>
 #include <queue>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <thread>
+#include <tuple>
 #include <unistd.h>
 
 namespace gathost {
@@ -978,6 +980,132 @@ MultiGpu::MultiGpu(int nGpus)
 MultiGpu::~MultiGpu()
 {
     for (gat_ctx *c : ctx) gat_destroy(c);
+}
+
+// ------------------------------------------------------------------ chainRemovePartialOverlaps
+namespace {
+struct XBlock { int tStart, tEnd, qStart, qEnd; };
+struct XKey {
+    uint32_t tSeq, qSeq; int lt, lq, rt, rq, ov;
+    bool operator<(const XKey &o) const
+    {
+        return std::tie(tSeq, qSeq, lt, lq, rt, rq, ov) < std::tie(o.tSeq, o.qSeq, o.lt, o.lq, o.rt, o.rq, o.ov);
+    }
+};
+typedef std::map<XKey, std::pair<int, int>> XCache;     // -> (crossover, scoreAdjustment); crossover -1 = asked, not answered yet
+
+// One chain, chainConnect.c:255-344.  Returns false if a crossover was missing from the cache (its key is in `want`).
+bool trimChain(const ChainHead &h, uint32_t tSeq, uint32_t qSeq, std::vector<XBlock> &bl, XCache &cache, std::vector<XKey> &want)
+{
+    for (size_t i = 1; i < bl.size(); i++)      // checkChainIncreases, :182-198
+        if (bl[i - 1].qStart >= bl[i].qStart || bl[i - 1].tStart >= bl[i].tStart)
+            fail("a (%d %d) not before b (%d %d) %s", bl[i - 1].qStart, bl[i - 1].tStart, bl[i].qStart, bl[i].tStart, "before removePartialOverlaps");
+    for (;;) {
+        bool totalTrimA = false;
+        size_t a = 0, b = 1;
+        while (b < bl.size()) {
+            bool totalTrimB = false;
+            const int dq = bl[b].qStart - bl[a].qEnd, dt = bl[b].tStart - bl[a].tEnd;
+            if (dq < 0 || dt < 0) {
+                const int overlap = -std::min(dq, dt);
+                const int aSize = bl[a].qEnd - bl[a].qStart, bSize = bl[b].qEnd - bl[b].qStart;
+                if (overlap >= aSize || overlap >= bSize) totalTrimB = true;
+                else {
+                    const XKey k{tSeq, qSeq | (h.qStrand == '-' ? GAT_QSEQ_MINUS : 0u), bl[a].tEnd, bl[a].qEnd, bl[b].tStart, bl[b].qStart, overlap};
+                    auto it = cache.find(k);
+                    if (it == cache.end() || it->second.first < 0) {
+                        if (it == cache.end()) { cache[k] = std::make_pair(-1, 0); want.push_back(k); }
+                        return false;
+                    }
+                    const int crossover = it->second.first, invCross = overlap - crossover;
+                    bl[b].qStart += crossover; bl[b].tStart += crossover;
+                    bl[a].qEnd -= invCross; bl[a].tEnd -= invCross;
+                    if (bl[b].qEnd <= bl[b].qStart) totalTrimB = true;
+                    else if (bl[a].qEnd <= bl[a].qStart) totalTrimA = true;
+                }
+            }
+            if (totalTrimA) {           // removeNegativeBlocks, :214-240, then start over
+                bl.erase(std::remove_if(bl.begin(), bl.end(), [](const XBlock &x) { return x.qStart >= x.qEnd || x.tStart >= x.tEnd; }), bl.end());
+                break;
+            } else if (totalTrimB) bl.erase(bl.begin() + (long)b);
+            else { a = b; b++; }
+        }
+        if (!totalTrimA) break;
+        if (bl.size() < 2) break;
+    }
+    for (size_t i = 1; i < bl.size(); i++)      // checkChainGaps, :164-180
+        if (bl[i - 1].qEnd > bl[i].qStart || bl[i - 1].tEnd > bl[i].tStart)
+            fail("Negative gap between (%d %d - %d %d) and (%d %d - %d %d) %s", bl[i - 1].qStart, bl[i - 1].tStart, bl[i - 1].qEnd, bl[i - 1].tEnd,
+                 bl[i].qStart, bl[i].tStart, bl[i].qEnd, bl[i].tEnd, "after removePartialOverlaps");
+    for (const XBlock &x : bl)                  // checkStartBeforeEnd, :150-162
+        if (x.qStart >= x.qEnd || x.tStart >= x.tEnd)
+            fail("Start after end in (%d %d) to (%d %d) %s", x.qStart, x.tStart, x.qEnd, x.tEnd, "after removePartialOverlaps");
+    return true;
+}
+}  // namespace
+
+void removePartialOverlaps(gat_ctx *ctx, ChainSet &cs, const std::vector<uint32_t> &chainT, const std::vector<uint32_t> &chainQ)
+{
+    const size_t n = cs.chains.size();
+    auto original = [&](size_t c) {
+        const ChainHead &h = cs.chains[c];
+        std::vector<XBlock> bl(h.nBlocks);
+        for (uint64_t i = 0; i < h.nBlocks; i++) {
+            const gat_block &b = cs.blocks[h.firstBlock + i];
+            bl[i] = XBlock{b.tStart, b.tStart + (int)b.size, b.qStart, b.qStart + (int)b.size};
+        }
+        return bl;
+    };
+    XCache cache;
+    std::vector<XKey> want;
+    // first sweep, speculative: every overlapping neighbour pair as the file has it (later trims only change a pair's
+    // inputs after a block dried up, which is rare)
+    for (size_t c = 0; c < n; c++) {
+        const ChainHead &h = cs.chains[c];
+        const std::vector<XBlock> bl = original(c);
+        for (size_t i = 1; i < bl.size(); i++) {
+            const int dq = bl[i].qStart - bl[i - 1].qEnd, dt = bl[i].tStart - bl[i - 1].tEnd;
+            if (dq >= 0 && dt >= 0) continue;
+            const int overlap = -std::min(dq, dt);
+            if (overlap >= bl[i - 1].qEnd - bl[i - 1].qStart || overlap >= bl[i].qEnd - bl[i].qStart) continue;
+            const XKey k{chainT[c], chainQ[c] | (h.qStrand == '-' ? GAT_QSEQ_MINUS : 0u), bl[i - 1].tEnd, bl[i - 1].qEnd, bl[i].tStart, bl[i].qStart, overlap};
+            if (cache.emplace(k, std::make_pair(-1, 0)).second) want.push_back(k);
+        }
+    }
+    std::vector<std::vector<XBlock>> done(n);
+    std::vector<char> finished(n, 0);
+    for (;;) {
+        if (!want.empty()) {
+            std::vector<gat_xpair> pairs(want.size());
+            std::vector<int32_t> pos(want.size()), adj(want.size());
+            for (size_t i = 0; i < want.size(); i++)
+                pairs[i] = gat_xpair{want[i].tSeq, want[i].qSeq, want[i].lt, want[i].lq, want[i].rt, want[i].rq, want[i].ov};
+            if (gat_crossover(ctx, pairs.data(), pairs.size(), pos.data(), adj.data()) != GAT_OK) fail("%s", gat_last_error());
+            for (size_t i = 0; i < want.size(); i++) cache[want[i]] = std::make_pair((int)pos[i], (int)adj[i]);
+            want.clear();
+        }
+        bool pending = false;
+        for (size_t c = 0; c < n; c++) {
+            if (finished[c]) continue;
+            std::vector<XBlock> bl = original(c);
+            if (trimChain(cs.chains[c], chainT[c], chainQ[c], bl, cache, want)) { done[c] = std::move(bl); finished[c] = 1; }
+            else pending = true;
+        }
+        if (!pending) break;
+    }
+    std::vector<gat_block> blocks;
+    blocks.reserve(cs.blocks.size());
+    for (size_t c = 0; c < n; c++) {
+        ChainHead &h = cs.chains[c];
+        h.firstBlock = blocks.size();
+        for (const XBlock &x : done[c]) blocks.push_back(gat_block{x.tStart, x.qStart, (uint32_t)(x.tEnd - x.tStart)});
+        h.nBlocks = done[c].size();
+        if (!done[c].empty()) {                 // setChainBounds, :242-253
+            h.tStart = done[c].front().tStart; h.qStart = done[c].front().qStart;
+            h.tEnd = done[c].back().tEnd; h.qEnd = done[c].back().qEnd;
+        }
+    }
+    cs.blocks.swap(blocks);
 }
 
 // CUDA context creation takes most of a second: tools start it first and parse their inputs meanwhile.

@@ -153,6 +153,12 @@ struct MultiGpu {
     void score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local);
 };
 
+// chainRemovePartialOverlaps (kent/src/lib/chainConnect.c:255-344) for every chain of a set: where adjacent blocks
+// overlap, the crossover point comes from the device (gat_crossover, one batch per sweep), the trimming and the rare
+// removal of a dried-up block follow the reference step by step.  chainT / chainQ: sequence index per chain (as
+// uploaded).  Blocks, block counts and bounds of `cs` are rewritten in place.
+void removePartialOverlaps(gat_ctx *ctx, ChainSet &cs, const std::vector<uint32_t> &chainT, const std::vector<uint32_t> &chainQ);
+
 // Starts creating the CUDA contexts on a background thread; get() waits for them.
 struct GpuStarter {
     struct Impl;

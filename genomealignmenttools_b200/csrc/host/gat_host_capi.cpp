@@ -60,6 +60,13 @@ extern "C" int gathost_chains_subset(const gathost_chains *c, uint64_t ix, int s
     return 1;
 }
 
+extern "C" int gathost_chains_remove_partial_overlaps(gathost_chains *c, gat_ctx *ctx, const uint32_t *chainT, const uint32_t *chainQ)
+{
+    const size_t n = c->cs.chains.size();
+    GUARD(removePartialOverlaps(ctx, c->cs, std::vector<uint32_t>(chainT, chainT + n), std::vector<uint32_t>(chainQ, chainQ + n));
+          buildRecords(c->cs, c->wl); return 0;, -1)
+}
+
 struct gathost_twobit { TwoBitFile tb; explicit gathost_twobit(const char *p) : tb(p) {} };
 extern "C" gathost_twobit *gathost_twobit_open(const char *path) { GUARD(return new gathost_twobit(path);, nullptr) }
 extern "C" void gathost_twobit_close(gathost_twobit *t) { delete t; }

@@ -37,6 +37,11 @@ int gathost_chains_head(const gathost_chains *c, uint64_t ix, double *score, con
 int gathost_chains_subset(const gathost_chains *c, uint64_t ix, int subStart, int subEnd, uint64_t *firstBlock,
                           uint64_t *nBlocks, int32_t *clipStart, int32_t *clipEnd, int64_t *aliBases);
 
+/* chainRemovePartialOverlaps (kent/src/lib/chainConnect.c:255-344) on every chain of the set, crossover points from
+ * gat_crossover() on `ctx` (genomes and scoring loaded); chainT / chainQ = sequence index per chain as uploaded.
+ * Blocks, counts and bounds are rewritten in place (read them back with gathost_chains_head / _blocks). */
+int gathost_chains_remove_partial_overlaps(gathost_chains *c, gat_ctx *ctx, const uint32_t *chainT, const uint32_t *chainQ);
+
 /* .2bit container (kent/src/lib/twoBit.c:422-650). */
 typedef struct gathost_twobit gathost_twobit;
 gathost_twobit *gathost_twobit_open(const char *path);

@@ -152,3 +152,24 @@ for (i=0; i<n; ++i)
     cBlockFindCrossover(&left, &right, qSeq, tSeq, overlap[i], scoreScheme->matrix, &pos[i], &adjust[i]);
     }
 }
+
+int ref_remove_partial_overlaps(int chainIx)
+/* chainRemovePartialOverlaps (kent/src/lib/chainConnect.c:255-344) on a loaded chain, in place; returns its block count. */
+{
+struct chain *chain = chains[chainIx];
+struct dnaSeq *qSeq = getSeqFromHash(chain->qName, chain->qStrand, qSeqHash);
+struct dnaSeq *tSeq = getSeqFromHash(chain->tName, '+', tSeqHash);
+chainRemovePartialOverlaps(chain, qSeq, tSeq, scoreScheme->matrix);
+return slCount(chain->blockList);
+}
+
+void ref_chain_blocks(int chainIx, int *tStart, int *qStart, int *size, int *bounds)
+/* Blocks and bounds (tStart tEnd qStart qEnd) of a loaded chain. */
+{
+struct chain *chain = chains[chainIx];
+struct cBlock *b;
+int i = 0;
+for (b = chain->blockList; b != NULL; b = b->next, ++i)
+    { tStart[i] = b->tStart; qStart[i] = b->qStart; size[i] = b->tEnd - b->tStart; }
+bounds[0] = chain->tStart; bounds[1] = chain->tEnd; bounds[2] = chain->qStart; bounds[3] = chain->qEnd;
+}

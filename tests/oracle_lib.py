@@ -159,6 +159,14 @@ class KentRef:
                                pos.ctypes.data, adj.ctypes.data)
         return pos, adj
 
+    def remove_partial_overlaps(self, ix):
+        """chainRemovePartialOverlaps on loaded chain ix; returns (blocks as (n,3) int array, bounds)."""
+        n = self.lib.ref_remove_partial_overlaps(int(ix))
+        t = np.zeros(n, dtype=np.int32); q = np.zeros(n, dtype=np.int32); sz = np.zeros(n, dtype=np.int32); b = np.zeros(4, dtype=np.int32)
+        self.lib.ref_chain_blocks.argtypes = [_i32] + [_vp] * 4
+        self.lib.ref_chain_blocks(int(ix), t.ctypes.data, q.ctypes.data, sz.ctypes.data, b.ctypes.data)
+        return np.stack([t, q, sz], axis=1), b
+
     def score_sub(self, ix, s, e):
         ix = np.ascontiguousarray(ix, dtype=np.int32); s = np.ascontiguousarray(s, dtype=np.int32)
         e = np.ascontiguousarray(e, dtype=np.int32)

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 from genomealignmenttools_b200 import ChainScorer, Scoring, ScoreScheme, GapCalc, GatError, chainio, synth
 from genomealignmenttools_b200.twobit import PackedGenome
+from genomealignmenttools_b200.records import job_block_counts
 from genomealignmenttools_b200.records import (JOB_DTYPE, BLOCK_DTYPE, NRUN_DTYPE, NO_CLIP_START, NO_CLIP_END,
                                                BLOCK_JOINED, QSEQ_MINUS, ali_bases)
 import make_golden_helpers as helpers
@@ -309,6 +310,55 @@ def test_crossover_matches_oracle(oracle, tmp_path):
             sc.crossover(bad)
         pos, adj = sc.crossover(np.zeros(0, dtype=XPAIR_DTYPE))
         assert len(pos) == 0
+
+
+def test_remove_partial_overlaps_matches_reference(kentref, tmp_path):
+    """gathost::removePartialOverlaps (host loop + gat_crossover batches) against the unmodified
+    chainRemovePartialOverlaps (kent chainConnect.c:255-344): chains whose neighbouring blocks overlap by a few bases,
+    by most of a block, or swallow a block whole; both strands."""
+    if kentref is None:
+        pytest.skip("oracle/_ref not built")
+    import ctypes
+    import hostlib
+    w, tn, qn = small_world(seed=33, n_blocks=4000, max_chain_blocks=60, max_len=1500)
+    rng = np.random.default_rng(2)
+    counts = job_block_counts(w.jobs, w.total)
+    blocks = w.blocks.copy()
+    for j in range(len(w.jobs)):
+        fb, nb = int(w.jobs[j]["firstBlock"]), int(counts[j])
+        for i in range(fb, fb + nb - 1):
+            if rng.random() < 0.4:
+                nxt = blocks[i + 1]
+                gap = min(int(nxt["tStart"]) - (int(blocks[i]["tStart"]) + int(blocks[i]["size"])), int(nxt["qStart"]) - (int(blocks[i]["qStart"]) + int(blocks[i]["size"])))
+                room = int(nxt["size"]) - 1 if rng.random() < 0.8 else int(nxt["size"]) + 3     # sometimes past the whole next block
+                ext = gap + int(rng.integers(1, max(2, room)))
+                # starts must keep increasing (checkChainIncreases): the extension moves only this block's end
+                blocks[i]["size"] = int(blocks[i]["size"]) + max(0, ext)
+    w2 = synth.Workload(w.t, w.q, w.jobs, w.total, blocks)
+    paths = helpers.write_case(w2, tn, qn, tmp_path)
+    kentref.set_scoring(None, "loose")
+    n = kentref.open(paths["t"], paths["q"], paths["chain"])
+    lib = hostlib.load()
+    cs = lib.gathost_chains_read(paths["chain"].encode())
+    assert cs, lib.gathost_last_error()
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(Scoring(None, "loose"))
+        ct = np.ascontiguousarray(w.jobs["tSeq"], dtype=np.uint32); cq = np.ascontiguousarray(w.jobs["qSeq"] & 0x7FFFFFFF, dtype=np.uint32)
+        lib.gathost_chains_remove_partial_overlaps.argtypes = [ctypes.c_void_p] * 4
+        rc = lib.gathost_chains_remove_partial_overlaps(cs, sc.ctx, ct.ctypes.data, cq.ctypes.data)
+        assert rc == 0, lib.gathost_last_error()
+    heads = hostlib.chain_heads(lib, cs)
+    ours = hostlib.chain_blocks(lib, cs)
+    changed = 0
+    for c in range(n):
+        ref_blocks, bounds = kentref.remove_partial_overlaps(c)
+        h = heads[c]
+        mine = ours[h["firstBlock"]:h["firstBlock"] + h["nBlocks"]]
+        got = np.stack([mine["tStart"], mine["qStart"], mine["size"].astype(np.int32)], axis=1)
+        assert np.array_equal(got, ref_blocks), c
+        assert [h["tStart"], h["tEnd"], h["qStart"], h["qEnd"]] == list(bounds)
+        changed += int(len(ref_blocks) != counts[c])
+    assert changed > 5          # some blocks dried up and were removed
 
 
 def test_resident_worklist_matches_one_shot():
