@@ -37,7 +37,7 @@ constexpr int GROUP_BASES = 128;       // sequences start on a 32-byte sector bo
 // Idle lanes of the last item round read up to 31 words beyond (or, on '-', before) the last block of a warp,
 // and funnel shifts read one word past a window: 36 words of slack at both ends of the genome buffers.
 constexpr int PAD_FRONT_GROUPS = 9;
-constexpr int PAD_BACK_GROUPS = 10;
+constexpr int PAD_BACK_GROUPS = 26;     // + 32 * GAT_AHEAD words of read-ahead behind a continued record
 constexpr int NWIN_SHIFT = 8;          // N summary: one bit per 256 bases
 
 constexpr int ERR_SEQ = 1, ERR_BLOCKIDX = 2, ERR_COORD = 4, ERR_TOOLONG = 8, ERR_CSR = 16;
@@ -376,7 +376,7 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
 }
 
 // ------------------------------------------------------------------ the scoring kernel
-// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | mayN<<11; excl: items of the warp before this block
+// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | continued-by-next-record<<10 | mayN<<11; excl: items of the warp before this block
 struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 
 #ifndef GAT_MIN_CTAS
@@ -384,6 +384,9 @@ struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 #endif
 #ifndef GAT_P1_UNROLL
 #define GAT_P1_UNROLL 1
+#endif
+#ifndef GAT_AHEAD
+#define GAT_AHEAD 2       // item rounds of L2 read-ahead inside long blocks (0 = none)
 #endif
 #ifndef GAT_PREFETCH
 #define GAT_PREFETCH 2      // bit 1: fetch the next sub-tile's job and record while the current one is processed
@@ -413,6 +416,8 @@ __device__ __forceinline__ void clipBlock(const gat_block &b, int clipStart, int
     if (te > clipEnd) te = clipEnd;
     len = te - ts;
 }
+
+__device__ __forceinline__ bool isEndOfJob(uint32_t headWord, int lane) { return lane < 31 && ((headWord >> (lane + 1)) & 1u) != 0; }
 
 template <typename T> __device__ __forceinline__ long long finalLocal(const TupT<T> &t)
 {   // a job's running score ends at max(c, d) (entered with 0) and its last peak test is still due
@@ -602,6 +607,9 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             uint32_t flag = v < vEnd ? (8u | (isHead ? 1u : 0u) | (isEnd ? 2u : 0u)) : 0u;
             // chainFastSubsetOnT clip (chain.c:513-522)
             const bool joined = (rec.size & GAT_BLOCK_JOINED) != 0;
+            // is the record after mine its continuation (a long block cut by the host)?  Then the genome words behind
+            // my window are the next record's: the item loop may read ahead past my end.  (Lane 31 does not know.)
+            const bool continued = __shfl_down_sync(FULL, (int)(ok && joined), 1) != 0 && lane < 31 && !isEndOfJob(hw, lane);
             int ts = rec.tStart, qs = rec.qStart;
             int te = ts + (int)(rec.size & 0x7fffffffu);
             const int cut = job.clipStart > ts ? job.clipStart - ts : 0;
@@ -659,7 +667,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             const uint32_t lb = __ballot_sync(FULL, listed);
             if (listed) {
                 const int slot = nSlots + __popc(lb & (leMask >> 1));
-                sStage[warp][slot] = StageRec{tW + 1, qW + 1, (n - 32) | ((tSh | (qSh << 5) | (mayN ? 0x800u : 0u)) << 20), 0u};
+                sStage[warp][slot] = StageRec{tW + 1, qW + 1, (n - 32) | ((tSh | (qSh << 5) | (continued ? 0x400u : 0u) | (mayN ? 0x800u : 0u)) << 20), 0u};
                 sEx[warp * TILE + slot] = (n - 1) >> 5;             // item count for now
                 sSlotV[warp * TILE + slot] = (unsigned char)(sub * 32 + lane);
             }
@@ -728,6 +736,9 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
                 const uint2 *tp = tPlanes + (rec.tW + k);                                                   \
                 const uint2 *qp = qPlanes + (rec.qW + k);                                                   \
                 W0 = __ldg(tp); W1 = __ldg(tp + 1); W2 = __ldg(qp); W3 = __ldg(qp + 1);                     \
+                if (GAT_AHEAD && (LEFT > 1024 * GAT_AHEAD || ((MISC & 0x400u) && LEFT > 0))) {   /* a long block (or one that goes on in the next record): ask L2 for the words GAT_AHEAD rounds from now */ \
+                    prefetchL2(tp + 32 * GAT_AHEAD); prefetchL2(qp + 32 * GAT_AHEAD);                       \
+                }                                                                                           \
             }
 #define GAT_CONSUME(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                      \
             {                                                                                               \
