@@ -564,6 +564,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     // not four); pass A2 turns records into window descriptors and asks L2 for the first and last sector of
     // every window; pass B then scores each block's first 32 bases out of L2 and builds the item list.
     bool anyN = false;
+    bool anyLong = false;               // some block of this warp is worth reading ahead for
     int nSlots = 0;                     // blocks of this warp with more than 32 bases: they get a slot in the item list
     const uint32_t leMask = 0xffffffffu >> (31 - lane);
     {
@@ -631,6 +632,12 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             // without bases read the front padding
             const uint2 ta = __ldg(P.t.planes + tW), tb = __ldg(P.t.planes + tW + 1);
             const uint2 qa = __ldg(P.q.planes + qW), qb = __ldg(P.q.planes + qW + 1);
+#if GAT_PREFETCH & 1
+            if (n > 32) {       // the item loop reads the rest of the block soon: ask L2 for its last sector now
+                prefetchL2(P.t.planes + tW + ((tSh + n - 1) >> 5));
+                prefetchL2(P.q.planes + qW + ((qSh + n - 1) >> 5));
+            }
+#endif
             bool mayN = false;
             if (n) mayN = wordsTouchN(P.t.nwin, tW, tW + ((tSh + n - 1) >> 5)) || wordsTouchN(P.q.nwin, qW, qW + ((qSh + n - 1) >> 5));
             // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
@@ -662,6 +669,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             }
             sScore[v] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
             anyN |= mayN;
+            anyLong |= continued || n > 1024u * GAT_AHEAD;
             // what is left of the block joins the warp's item list
             const bool listed = n > 32;
             const uint32_t lb = __ballot_sync(FULL, listed);
@@ -676,6 +684,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
         if (errAcc) atomicOr(P.err, errAcc);
     }
     anyN = __any_sync(FULL, anyN);
+    anyLong = __any_sync(FULL, anyLong);
     GAT_TICK(1)
 
     // ---- phase 2: what is left of the warp's blocks as one list of 32-base items, dealt to lanes round
@@ -736,7 +745,7 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
                 const uint2 *tp = tPlanes + (rec.tW + k);                                                   \
                 const uint2 *qp = qPlanes + (rec.qW + k);                                                   \
                 W0 = __ldg(tp); W1 = __ldg(tp + 1); W2 = __ldg(qp); W3 = __ldg(qp + 1);                     \
-                if (GAT_AHEAD && (LEFT > 1024 * GAT_AHEAD || ((MISC & 0x400u) && LEFT > 0))) {   /* a long block (or one that goes on in the next record): ask L2 for the words GAT_AHEAD rounds from now */ \
+                if (GAT_AHEAD && anyLong && (LEFT > 1024 * GAT_AHEAD || ((MISC & 0x400u) && LEFT > 0))) {   /* a long block (or one that goes on in the next record): ask L2 for the words GAT_AHEAD rounds from now */ \
                     prefetchL2(tp + 32 * GAT_AHEAD); prefetchL2(qp + 32 * GAT_AHEAD);                       \
                 }                                                                                           \
             }
