@@ -368,7 +368,8 @@ def main():
     sc.load_genome("t", w.t)
     sc.load_genome("q", w.q)
     sc.set_scoring(Scoring(None, "medium"))
-    log("[rank %d] genomes resident in HBM after %.1f s (NUMA node %s)" % (rank, time.time() - t0, numa))
+    upload_s = time.time() - t0
+    log("[rank %d] genomes resident in HBM after %.1f s (NUMA node %s)" % (rank, upload_s, numa))
 
     # ---- device-resident timing (value)
     wl = sc.upload(w.jobs, w.total, w.blocks)
@@ -407,7 +408,7 @@ def main():
         lib.gat_debug_timing(out)
         wl.run(); sc.synchronize()
         lib.gat_debug_timing(out)
-        warps = ((w.total + 1023) // 1024) * 8
+        warps = (w.total + 127) // 128
         sys.stderr.write("phase clocks per warp: " + " ".join("%d" % (x // warps) for x in out) + "\n")
 
     # ---- end-to-end through the public call with pinned host buffers (e2e)
@@ -429,6 +430,13 @@ def main():
     e2e_wall_ms = (time.time() - tw0) * 1e3 / e2e_steps
     e2e_ms = max(e2.elapsed_time(e3) / e2e_steps, e2e_wall_ms)   # the call blocks: wall time is the honest one
     assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "e2e and resident results differ"
+    # where an end-to-end step goes (one extra, profiled call; not part of the timed region)
+    sc.set_profiling(True)
+    sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
+    st = sc.stats()
+    sc.set_profiling(False)
+    e2e_parts = {"h2d_ms": round(float(st["h2d_ms"]), 4), "kernels_ms": round(float(st["all_kernels_ms"]), 4),
+                 "d2h_and_sync_ms": round(max(0.0, e2e_ms - float(st["h2d_ms"]) - float(st["all_kernels_ms"])), 4)}
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     per_step_ms = ms / args.steps
@@ -461,14 +469,14 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
             "e2e": {"value": total_bp / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": int(w.jobs.nbytes + w.blocks.nbytes), "d2h_bytes_per_step": int(16 * len(w.jobs)),
-                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "parts_rank0": e2e_parts},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "kernel": "scoreChunksKernel",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": w.algorithmic_bytes()},
             "clocks": clocks,
-            "aligned_bp_per_gpu": w.aligned_bp, "chains_per_gpu": int(len(w.jobs)),
+            "aligned_bp_per_gpu": w.aligned_bp, "chains_per_gpu": int(len(w.jobs)), "genome_upload_s": round(upload_s, 3),
         }
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.time()
