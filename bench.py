@@ -411,41 +411,65 @@ def main():
         warps = (w.total + 127) // 128
         sys.stderr.write("phase clocks per warp: " + " ".join("%d" % (x // warps) for x in out) + "\n")
 
-    # ---- end-to-end through the public call with pinned host buffers (e2e)
-    pj, pb = PinnedArray(len(w.jobs), JOB_DTYPE), PinnedArray(len(w.blocks), BLOCK_DTYPE)
+    # ---- end-to-end through the public calls with pinned host buffers (e2e): every step copies the work-list in,
+    # runs the kernels and copies the scores out.  Headline: gat_score_compact(), the work-list as a .chain file
+    # stores it (size + gaps, 6 bytes per block; expanded on the device).  gat_score() with 12-byte absolute
+    # records is timed beside it.
+    from genomealignmenttools_b200.records import (pack_compact, split_long_blocks, CJOB_DTYPE, CBLOCK_DTYPE, CABS_DTYPE)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def time_calls(call):
+        for _ in range(2):
+            call()
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.time()
+        ea.record(stream)
+        for _ in range(e2e_steps):
+            call()
+        eb.record(stream)
+        barrier()
+        wall_ms = (time.time() - tw0) * 1e3 / e2e_steps
+        return max(ea.elapsed_time(eb) / e2e_steps, wall_ms)       # the calls block: wall time is the honest one
+
+    def parts_of(call):         # where a step goes (one extra, profiled call; not part of a timed region)
+        sc.set_profiling(True)
+        call()
+        st = sc.stats()
+        sc.set_profiling(False)
+        return float(st["h2d_ms"]), float(st["all_kernels_ms"])
+
     pg, pl = PinnedArray(len(w.jobs), np.int64), PinnedArray(len(w.jobs), np.int64)
+    pj, pb = PinnedArray(len(w.jobs), JOB_DTYPE), PinnedArray(len(w.blocks), BLOCK_DTYPE)
     pj.array[:] = w.jobs
     pb.array[:] = w.blocks
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tw0 = time.time()
-    e2.record(stream)
-    for _ in range(e2e_steps):
-        sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
-    e3.record(stream)
-    barrier()
-    e2e_wall_ms = (time.time() - tw0) * 1e3 / e2e_steps
-    e2e_ms = max(e2.elapsed_time(e3) / e2e_steps, e2e_wall_ms)   # the call blocks: wall time is the honest one
+    plain_call = lambda: sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
+    plain_ms = time_calls(plain_call)
     assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "e2e and resident results differ"
-    # where an end-to-end step goes (one extra, profiled call; not part of the timed region)
-    sc.set_profiling(True)
-    sc.score(pj.array, w.total, pb.array, pg.array, pl.array)
-    st = sc.stats()
-    sc.set_profiling(False)
-    e2e_parts = {"h2d_ms": round(float(st["h2d_ms"]), 4), "kernels_ms": round(float(st["all_kernels_ms"]), 4),
-                 "d2h_and_sync_ms": round(max(0.0, e2e_ms - float(st["h2d_ms"]) - float(st["all_kernels_ms"])), 4)}
+    plain_bytes = int(w.jobs.nbytes + w.blocks.nbytes)
+    pj.free(); pb.free()
+
+    cj, cb, ab, an = pack_compact(*split_long_blocks(w.jobs, w.total, w.blocks, 4096))
+    pins = [PinnedArray(len(a), d) for a, d in ((cj, CJOB_DTYPE), (cb, CBLOCK_DTYPE), (ab, CABS_DTYPE), (an, CABS_DTYPE))]
+    for pin, a in zip(pins, (cj, cb, ab, an)):
+        pin.array[:] = a
+    pg.array[:] = 0; pl.array[:] = 0
+    compact_call = lambda: sc.score_compact(pins[0].array, pins[1].array, pins[2].array, pins[3].array, pg.array, pl.array)
+    e2e_ms = time_calls(compact_call)
+    assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "compact e2e and resident results differ"
+    compact_bytes = int(cj.nbytes + cb.nbytes + ab.nbytes + an.nbytes)
+    h2d_ms, kern_ms = parts_of(compact_call)
+    e2e_parts = {"h2d_and_expand_ms": round(h2d_ms, 4), "kernels_ms": round(kern_ms, 4),
+                 "d2h_and_sync_ms": round(max(0.0, e2e_ms - h2d_ms - kern_ms), 4)}
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     per_step_ms = ms / args.steps
-    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes())],
+    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes()), plain_ms],
                          dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        per_step_ms, e2e_ms, kernel_ms = mx[0].item(), mx[1].item(), mx[2].item()
+        per_step_ms, e2e_ms, kernel_ms, plain_ms = mx[0].item(), mx[1].item(), mx[2].item(), mx[5].item()
         total_bp = sm[3].item()
     else:
         total_bp = float(w.aligned_bp)
@@ -468,8 +492,11 @@ def main():
             "steps": args.steps, "warmup": warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
             "e2e": {"value": total_bp / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": int(w.jobs.nbytes + w.blocks.nbytes), "d2h_bytes_per_step": int(16 * len(w.jobs)),
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "parts_rank0": e2e_parts},
+                    "h2d_bytes_per_step": compact_bytes, "d2h_bytes_per_step": int(16 * len(w.jobs)),
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "parts_rank0": e2e_parts,
+                    "call": "gat_score_compact: work-list as a .chain file stores it (6-byte size/gap blocks, 8-byte chains), expanded on the device",
+                    "plain_records": {"call": "gat_score: 12-byte absolute blocks, 24-byte jobs", "value": total_bp / (plain_ms * 1e-3) / 1e9,
+                                      "ms_per_step": plain_ms, "h2d_bytes_per_step": plain_bytes}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
@@ -492,7 +519,7 @@ def main():
                                         "sample": "oracle/_ref/ref_driver missing"}
         print(json.dumps(line))
     wl.free()
-    for p in (pj, pb, pg, pl):
+    for p in [pg, pl] + pins:
         p.free()
     sc.close()
     if world > 1:

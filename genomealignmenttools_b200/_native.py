@@ -12,7 +12,7 @@ SYMBOLS = [
     "gat_last_error", "gat_device_count", "gat_create", "gat_destroy", "gat_load_genome",
     "gat_set_scoring", "gat_score", "gat_worklist_create", "gat_worklist_run", "gat_worklist_results",
     "gat_worklist_destroy", "gat_synchronize", "gat_get_stats", "gat_set_profiling",
-    "gat_host_alloc", "gat_host_free", "gat_max_record_bases", "gat_crossover",
+    "gat_host_alloc", "gat_host_free", "gat_max_record_bases", "gat_crossover", "gat_score_compact",
 ]
 
 
@@ -57,6 +57,7 @@ def load():
     lib.gat_worklist_destroy.argtypes = [vp, vp]
     lib.gat_worklist_destroy.restype = None
     lib.gat_crossover.argtypes = [vp, vp, u64, vp, vp]
+    lib.gat_score_compact.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
     lib.gat_max_record_bases.argtypes = [vp]
     lib.gat_max_record_bases.restype = ctypes.c_uint32
     lib.gat_synchronize.argtypes = [vp]

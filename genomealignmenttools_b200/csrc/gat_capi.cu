@@ -60,6 +60,8 @@ struct gat_ctx {
     cudaEvent_t ev[6];
     gat_stats stats;
     gat_worklist *scratch = nullptr;   // device buffers of gat_score(), grown on demand and reused
+    void *compactBuf = nullptr;        // device staging of gat_score_compact(): jobs, blocks, abs, anchors
+    size_t compactCap = 0;
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
 };
@@ -132,6 +134,7 @@ extern "C" void gat_destroy(gat_ctx *ctx)
     ctx->genome[0].release();
     ctx->genome[1].release();
     if (ctx->scratch) { freeWorklistBuffers(ctx->scratch); delete ctx->scratch; }
+    cudaFree(ctx->compactBuf);
     cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense); cudaFree(ctx->err);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -587,6 +590,58 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
         cudaEventElapsedTime(&total, ctx->ev[4], ctx->ev[0]);
         ctx->stats.h2d_ms = total;
         ctx->stats.h2d_bytes = nJobs * sizeof(gat_job) + nBlocks * sizeof(gat_block);
+        ctx->stats.d2h_bytes = 2 * nJobs * sizeof(long long);
+    }
+    return rc;
+}
+
+extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_cblock *blocks, uint64_t nBlocks,
+                                 const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, int64_t *global, int64_t *local)
+{
+    if (!ctx) return fail(GAT_EINVAL, "gat_score_compact: NULL ctx");
+    if ((nJobs && (!jobs || !global || !local)) || (nBlocks && (!blocks || !anchors)) || (nAbs && !abs))
+        return fail(GAT_EINVAL, "gat_score_compact: NULL array");
+    if (!ctx->genome[0].loaded || !ctx->genome[1].loaded) return fail(GAT_ESTATE, "gat_score_compact: load both genomes first");
+    if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_score_compact: call gat_set_scoring first");
+    if (nJobs == 0) return GAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->scratch) ctx->scratch = new gat_worklist();
+    gat_worklist *wl = ctx->scratch;
+    int rc = shapeWorklist(ctx, wl, nJobs, nBlocks, nBlocks);
+    if (rc != GAT_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const uint64_t nGroups = (nBlocks + GAT_CGROUP - 1) / GAT_CGROUP;
+    auto up8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t oJobs = 0, oBlocks = oJobs + up8(nJobs * sizeof(gat_cjob)), oAbs = oBlocks + up8(nBlocks * sizeof(gat_cblock) + 8),
+                 oAnch = oAbs + up8(nAbs * sizeof(gat_cabs)), need = oAnch + up8(nGroups * sizeof(gat_cabs)) + 16;
+    if (need > ctx->compactCap) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(ctx->compactBuf); ctx->compactBuf = nullptr; ctx->compactCap = 0;
+        CU(cudaMalloc(&ctx->compactBuf, need + need / 8));
+        ctx->compactCap = need + need / 8;
+    }
+    char *base = static_cast<char *>(ctx->compactBuf);
+    const bool prof = ctx->profiling;
+    if (prof) cudaEventRecord(ctx->ev[4], st);
+    CU(cudaMemcpyAsync(base + oJobs, jobs, nJobs * sizeof(gat_cjob), cudaMemcpyHostToDevice, st));
+    if (nBlocks) CU(cudaMemcpyAsync(base + oBlocks, blocks, nBlocks * sizeof(gat_cblock), cudaMemcpyHostToDevice, st));
+    if (nAbs) CU(cudaMemcpyAsync(base + oAbs, abs, nAbs * sizeof(gat_cabs), cudaMemcpyHostToDevice, st));
+    if (nGroups) CU(cudaMemcpyAsync(base + oAnch, anchors, nGroups * sizeof(gat_cabs), cudaMemcpyHostToDevice, st));
+    expandJobsKernel<<<(unsigned)((nJobs + 255) / 256), 256, 0, st>>>(reinterpret_cast<const gat_cjob *>(base + oJobs), nJobs, wl->jobs);
+    if (nGroups)
+        expandBlocksKernel<<<(unsigned)nGroups, CX_TPB, 0, st>>>(reinterpret_cast<const gat_cblock *>(base + oBlocks), nBlocks,
+                                                                reinterpret_cast<const gat_cabs *>(base + oAbs), nAbs,
+                                                                reinterpret_cast<const gat_cabs *>(base + oAnch), wl->blocks, ctx->err);
+    CU(cudaGetLastError());
+    rc = gat_worklist_run(ctx, wl);
+    if (rc == GAT_OK) ctx->stats.kernel_launches += 2;
+    if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[5], st);
+    if (rc == GAT_OK) rc = gat_worklist_results(ctx, wl, global, local);
+    if (rc == GAT_OK && prof) {
+        float total = 0;
+        cudaEventElapsedTime(&total, ctx->ev[4], ctx->ev[0]);
+        ctx->stats.h2d_ms = total;          // copies + the two expansion kernels
+        ctx->stats.h2d_bytes = nJobs * sizeof(gat_cjob) + nBlocks * sizeof(gat_cblock) + nAbs * sizeof(gat_cabs) + nGroups * sizeof(gat_cabs);
         ctx->stats.d2h_bytes = 2 * nJobs * sizeof(long long);
     }
     return rc;

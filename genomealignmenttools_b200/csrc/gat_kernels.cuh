@@ -1018,6 +1018,86 @@ __global__ void revCompKernel(const uint32_t *__restrict__ seqSize, const long l
     if (rn) atomicOr(&nwin[(n >> 3) >> 5], 1u << ((n >> 3) & 31));
 }
 
+// ------------------------------------------------------------------ compact work-list -> records
+// gat_score_compact: 6-byte delta-coded blocks become gat_block records.  One CTA per group of GAT_CGROUP records;
+// a record's start is its predecessor's end plus the gap in front of it, unless it is flagged absolute (chain start,
+// oversized gap) or opens the group (anchor): a segmented prefix sum, four records per thread, one warp scan, one
+// pass over the warps.
+constexpr int CX_TPB = GAT_CGROUP / 4;
+struct CxSeg { int t, q; bool abs; };       // start of the last record seen (abs) or sum of the steps so far
+__device__ __forceinline__ CxSeg cxCombine(const CxSeg &l, const CxSeg &r) { return r.abs ? r : CxSeg{l.t + r.t, l.q + r.q, l.abs}; }
+
+__global__ void __launch_bounds__(CX_TPB)
+expandBlocksKernel(const gat_cblock *__restrict__ cb, unsigned long long nBlocks, const gat_cabs *__restrict__ absTab,
+                   unsigned long long nAbs, const gat_cabs *__restrict__ anchors, gat_block *__restrict__ out, int *__restrict__ err)
+{
+    __shared__ CxSeg sWarp[CX_TPB / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long g0 = (unsigned long long)blockIdx.x * GAT_CGROUP, r0 = g0 + 4ull * tid;
+    // my four records, and the size of the record in front of them (its end is where my first step starts)
+    uint32_t size[4], dt[4], dq[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool in = r0 + k < nBlocks;
+        const uint16_t *p = reinterpret_cast<const uint16_t *>(cb + (in ? r0 + k : 0));
+        size[k] = in ? __ldg(p) : 0u; dt[k] = in ? __ldg(p + 1) : 0u; dq[k] = in ? __ldg(p + 2) : 0u;
+    }
+    uint32_t prevSize = 0;
+    if (tid > 0 && r0 - 1 < nBlocks) prevSize = __ldg(reinterpret_cast<const uint16_t *>(cb + r0 - 1)) & GAT_CBLOCK_MAX_SIZE;
+    // per record: step from the previous record's start (or an absolute start); running fold inside the thread
+    CxSeg rec[4];
+    CxSeg acc{0, 0, false};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        CxSeg e;
+        const bool first = tid == 0 && k == 0;
+        if (first) { const gat_cabs a = anchors[blockIdx.x]; e = CxSeg{a.tStart, a.qStart, true}; }
+        else if (size[k] & GAT_CBLOCK_ABS) {
+            const unsigned long long ix = (unsigned long long)dt[k] | ((unsigned long long)dq[k] << 16);
+            if (ix < nAbs) { const gat_cabs a = absTab[ix]; e = CxSeg{a.tStart, a.qStart, true}; }
+            else { atomicOr(err, ERR_BLOCKIDX); e = CxSeg{0, 0, true}; }
+        } else {
+            const int before = (int)(k == 0 ? prevSize : (size[k - 1] & GAT_CBLOCK_MAX_SIZE));
+            e = CxSeg{before + (int)dt[k], before + (int)dq[k], false};
+        }
+        acc = k == 0 ? e : cxCombine(acc, e);
+        rec[k] = acc;                               // relative to whatever precedes the thread
+    }
+    // exclusive scan of the threads' folds: warp, then across warps
+    CxSeg inc = acc;
+    for (int off = 1; off < 32; off <<= 1) {
+        CxSeg o{__shfl_up_sync(FULL, inc.t, off), __shfl_up_sync(FULL, inc.q, off), __shfl_up_sync(FULL, (int)inc.abs, off) != 0};
+        if (lane >= off) inc = cxCombine(o, inc);
+    }
+    if (lane == 31) sWarp[warp] = inc;
+    CxSeg carry{__shfl_up_sync(FULL, inc.t, 1), __shfl_up_sync(FULL, inc.q, 1), __shfl_up_sync(FULL, (int)inc.abs, 1) != 0};
+    if (lane == 0) carry = CxSeg{0, 0, false};
+    __syncthreads();
+    CxSeg before{0, 0, false};
+    for (int w = 0; w < warp; w++) before = cxCombine(before, sWarp[w]);
+    carry = cxCombine(before, carry);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (r0 + k >= nBlocks) break;
+        const CxSeg s = cxCombine(carry, rec[k]);   // absolute: the group's first record is
+        uint32_t *o = reinterpret_cast<uint32_t *>(out + r0 + k);
+        o[0] = (uint32_t)s.t; o[1] = (uint32_t)s.q;
+        o[2] = (size[k] & GAT_CBLOCK_MAX_SIZE) | ((size[k] & GAT_CBLOCK_JOINED) ? GAT_BLOCK_JOINED : 0u);
+    }
+}
+
+__global__ void expandJobsKernel(const gat_cjob *__restrict__ cj, unsigned long long nJobs, gat_job *__restrict__ out)
+{
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nJobs) return;
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(cj + j));
+    const uint32_t tSeq = v.y & 0xffffu, q = v.y >> 16;
+    uint2 *o = reinterpret_cast<uint2 *>(out + j);
+    o[0] = make_uint2(tSeq, (q & 0x7fffu) | ((q & GAT_CJOB_MINUS) ? GAT_QSEQ_MINUS : 0u));
+    o[1] = make_uint2(v.x, v.x);                                        // firstBlock = blockPtr: whole chains
+    o[2] = make_uint2((uint32_t)GAT_NO_CLIP_START, (uint32_t)GAT_NO_CLIP_END);
+}
+
 // ------------------------------------------------------------------ crossover of overlapping blocks
 // cBlockFindCrossover (kent/src/lib/chainConnect.c:61-105), one thread per pair.  With L[i], R[i] the scores of base i
 // of the overlap in the left / right block, the reference starts from sum(R), adds L[i] - R[i] base by base and keeps

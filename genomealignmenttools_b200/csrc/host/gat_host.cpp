@@ -1134,12 +1134,67 @@ GpuStarter::~GpuStarter()
     delete impl;
 }
 
+// The work-list of whole chains as gat_score_compact takes it (include/gat.h): per block its size and the gap in front of
+// it, absolute starts only where a chain begins or a gap does not fit 16 bits.  False if the list does not qualify
+// (clipped or shared-record jobs, records beyond GAT_CBLOCK_MAX_SIZE, more than 32768 sequences).
+bool packCompact(const WorkList &wl, CompactWorkList &out)
+{
+    const size_t nJobs = wl.jobs.size(), n = wl.blocks.size();
+    if (wl.totalJobBlocks != n) return false;
+    out.jobs.resize(nJobs);
+    for (size_t j = 0; j < nJobs; j++) {
+        const gat_job &job = wl.jobs[j];
+        if (job.firstBlock != job.blockPtr || job.clipStart != GAT_NO_CLIP_START || job.clipEnd != GAT_NO_CLIP_END) return false;
+        if (job.tSeq > 0xffffu || (job.qSeq & 0x7fffffffu) > 0x7fffu) return false;
+        out.jobs[j] = gat_cjob{job.blockPtr, (uint16_t)job.tSeq, (uint16_t)((job.qSeq & 0x7fffu) | ((job.qSeq >> 31) ? GAT_CJOB_MINUS : 0u))};
+    }
+    out.blocks.resize(n);
+    out.abs.clear();
+    out.anchors.resize((n + GAT_CGROUP - 1) / GAT_CGROUP);
+    size_t nextJob = 0;
+    for (size_t i = 0; i < n; i++) {
+        const gat_block &b = wl.blocks[i];
+        const uint32_t size = b.size & 0x7fffffffu;
+        if (size > GAT_CBLOCK_MAX_SIZE) return false;
+        bool isAbs = false;
+        while (nextJob < nJobs && wl.jobs[nextJob].blockPtr <= i) {        // a chain starts here (empty jobs start nothing)
+            const uint64_t end = nextJob + 1 < nJobs ? wl.jobs[nextJob + 1].blockPtr : n;
+            if (wl.jobs[nextJob].blockPtr == i && end > i) isAbs = true;
+            nextJob++;
+        }
+        long long dt = 0, dq = 0;
+        if (i > 0) {
+            const gat_block &p = wl.blocks[i - 1];
+            const long long ps = p.size & 0x7fffffffu;
+            dt = (long long)b.tStart - ((long long)p.tStart + ps);
+            dq = (long long)b.qStart - ((long long)p.qStart + ps);
+        } else isAbs = true;
+        if (dt < 0 || dt > 0xffff || dq < 0 || dq > 0xffff) isAbs = true;
+        uint16_t s16 = (uint16_t)(size | ((b.size & GAT_BLOCK_JOINED) ? GAT_CBLOCK_JOINED : 0u));
+        if (isAbs) {
+            const uint64_t ix = out.abs.size();
+            if (ix >> 32) return false;
+            out.abs.push_back(gat_cabs{b.tStart, b.qStart});
+            out.blocks[i] = gat_cblock{(uint16_t)(s16 | GAT_CBLOCK_ABS), (uint16_t)(ix & 0xffff), (uint16_t)(ix >> 16)};
+        } else out.blocks[i] = gat_cblock{s16, (uint16_t)dt, (uint16_t)dq};
+        if (i % GAT_CGROUP == 0) out.anchors[i / GAT_CGROUP] = gat_cabs{b.tStart, b.qStart};
+    }
+    return true;
+}
+
 void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local)
 {
     global.assign(wl.jobs.size(), 0);
     local.assign(wl.jobs.size(), 0);
     if (wl.jobs.empty()) return;
     if (ctx.size() == 1) {
+        CompactWorkList cw;
+        if (packCompact(wl, cw)) {      // whole chains (scoreChain): half the bytes over PCIe
+            if (gat_score_compact(ctx[0], cw.jobs.data(), cw.jobs.size(), cw.blocks.data(), cw.blocks.size(), cw.abs.data(), cw.abs.size(),
+                                  cw.anchors.data(), global.data(), local.data()) != GAT_OK)
+                fail("%s", gat_last_error());
+            return;
+        }
         if (gat_score(ctx[0], wl.jobs.data(), wl.jobs.size(), wl.totalJobBlocks, wl.blocks.data(), wl.blocks.size(),
                       global.data(), local.data()) != GAT_OK)
             fail("%s", gat_last_error());

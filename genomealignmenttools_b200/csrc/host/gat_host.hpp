@@ -139,6 +139,12 @@ bool addSubChainJob(const ChainSet &cs, size_t chainIx, uint32_t tSeq, uint32_t 
 // only for chains whose blocks ascend and do not overlap on that side (chainAscends).
 bool chainAscends(const ChainSet &cs, size_t chainIx, bool onQ);
 uint64_t firstBlockEndingAfter(const ChainSet &cs, size_t chainIx, int pos, bool onQ);
+struct CompactWorkList {
+    std::vector<gat_cjob> jobs;
+    std::vector<gat_cblock> blocks;
+    std::vector<gat_cabs> abs, anchors;
+};
+bool packCompact(const WorkList &wl, CompactWorkList &out);
 // Greedy longest-processing-time split of jobs over `parts` GPUs by aligned bases.
 std::vector<std::vector<uint32_t>> shardJobs(const WorkList &wl, int parts);
 // Sub-work-list holding the given jobs (block records are shared, so only jobs are re-indexed).

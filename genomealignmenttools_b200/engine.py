@@ -85,6 +85,17 @@ class ChainScorer:
     def __exit__(self, *a):
         self.close()
 
+    def score_compact(self, cjobs, cblocks, ab, anchors, out_global=None, out_local=None):
+        """gat_score_compact: the work-list as records.pack_compact() makes it (about half the bytes of score())."""
+        from .records import CBLOCK_DTYPE, CJOB_DTYPE, CABS_DTYPE
+        cjobs = np.ascontiguousarray(cjobs, dtype=CJOB_DTYPE); cblocks = np.ascontiguousarray(cblocks, dtype=CBLOCK_DTYPE)
+        ab = np.ascontiguousarray(ab, dtype=CABS_DTYPE); anchors = np.ascontiguousarray(anchors, dtype=CABS_DTYPE)
+        g = out_global if out_global is not None else np.zeros(len(cjobs), dtype=np.int64)
+        l = out_local if out_local is not None else np.zeros(len(cjobs), dtype=np.int64)
+        self._check(self.lib.gat_score_compact(self.ctx, _ptr(cjobs), len(cjobs), _ptr(cblocks), len(cblocks), _ptr(ab), len(ab),
+                                               _ptr(anchors), _ptr(g), _ptr(l)))
+        return g, l
+
     def crossover(self, pairs):
         """cBlockFindCrossover (kent chainConnect.c:61-105) for a batch of overlapping block pairs (XPAIR_DTYPE):
         returns (pos, adjust) int32 arrays."""

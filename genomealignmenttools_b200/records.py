@@ -79,3 +79,76 @@ def split_long_blocks(jobs, total_job_blocks, blocks, max_bases=SPLIT_BASES):
 # gat_xpair (include/gat.h): one pair of overlapping adjacent blocks for gat_crossover
 XPAIR_DTYPE = np.dtype([("tSeq", "<u4"), ("qSeq", "<u4"), ("leftTEnd", "<i4"), ("leftQEnd", "<i4"),
                         ("rightTStart", "<i4"), ("rightQStart", "<i4"), ("overlap", "<i4")])
+
+
+# ---- compact work-list of gat_score_compact (include/gat.h): gat_cblock, gat_cjob, gat_cabs
+CBLOCK_DTYPE = np.dtype([("size", "<u2"), ("dt", "<u2"), ("dq", "<u2")])
+CJOB_DTYPE = np.dtype([("blockPtr", "<u4"), ("tSeq", "<u2"), ("qSeq", "<u2")])
+CABS_DTYPE = np.dtype([("tStart", "<i4"), ("qStart", "<i4")])
+assert CBLOCK_DTYPE.itemsize == 6 and CJOB_DTYPE.itemsize == 8 and CABS_DTYPE.itemsize == 8
+CBLOCK_ABS, CBLOCK_JOINED, CBLOCK_MAX_SIZE, CJOB_MINUS, CGROUP = 0x8000, 0x4000, 0x3FFF, 0x8000, 1024
+
+
+def pack_compact(jobs, total_job_blocks, blocks):
+    """Whole-chain work-list (firstBlock == blockPtr, no clip; records of at most CBLOCK_MAX_SIZE bases: run
+    split_long_blocks first) -> (cjobs, cblocks, abs, anchors) of gat_score_compact.  A block is stored as its size and
+    the gap in front of it -- the numbers of a .chain file's "size dt dq" lines -- unless it opens a chain or the gap
+    does not fit 16 bits; then its start goes to the absolute table."""
+    jobs = np.asarray(jobs); blocks = np.asarray(blocks)
+    n = int(total_job_blocks)
+    if n != len(blocks) or not np.array_equal(jobs["firstBlock"], jobs["blockPtr"]):
+        raise ValueError("pack_compact wants jobs that tile the block array")
+    if np.any(jobs["clipStart"] != NO_CLIP_START) or np.any(jobs["clipEnd"] != NO_CLIP_END):
+        raise ValueError("pack_compact wants unclipped jobs")
+    if np.any(jobs["tSeq"] > 0xFFFF) or np.any((jobs["qSeq"] & np.uint32(0x7FFFFFFF)) > 0x7FFF):
+        raise ValueError("pack_compact: sequence index beyond 16 bits")
+    size = (blocks["size"] & np.uint32(0x7FFFFFFF)).astype(np.int64)
+    if np.any(size > CBLOCK_MAX_SIZE):
+        raise ValueError("pack_compact: record longer than %d bases" % CBLOCK_MAX_SIZE)
+    joined = (blocks["size"] >> np.uint32(31)).astype(bool)
+    ts = blocks["tStart"].astype(np.int64); qs = blocks["qStart"].astype(np.int64)
+    dt = np.zeros(n, dtype=np.int64); dq = np.zeros(n, dtype=np.int64)
+    dt[1:] = ts[1:] - (ts[:-1] + size[:-1]); dq[1:] = qs[1:] - (qs[:-1] + size[:-1])
+    is_abs = (dt < 0) | (dt > 0xFFFF) | (dq < 0) | (dq > 0xFFFF)
+    counts = job_block_counts(jobs, n)
+    is_abs[jobs["blockPtr"][counts > 0].astype(np.int64)] = True      # first block of every chain
+    abs_ix = np.cumsum(is_abs) - 1
+    cb = np.zeros(n, dtype=CBLOCK_DTYPE)
+    cb["size"] = size | np.where(joined, CBLOCK_JOINED, 0) | np.where(is_abs, CBLOCK_ABS, 0)
+    cb["dt"] = np.where(is_abs, abs_ix & 0xFFFF, dt)
+    cb["dq"] = np.where(is_abs, abs_ix >> 16, dq)
+    if is_abs.sum() > 0 and abs_ix[-1] >> 32:
+        raise ValueError("pack_compact: more than 2^32 absolute records")
+    ab = np.zeros(int(is_abs.sum()), dtype=CABS_DTYPE)
+    ab["tStart"] = ts[is_abs]; ab["qStart"] = qs[is_abs]
+    anchors = np.zeros((n + CGROUP - 1) // CGROUP, dtype=CABS_DTYPE)
+    anchors["tStart"] = ts[::CGROUP]; anchors["qStart"] = qs[::CGROUP]
+    cj = np.zeros(len(jobs), dtype=CJOB_DTYPE)
+    cj["blockPtr"] = jobs["blockPtr"]; cj["tSeq"] = jobs["tSeq"]
+    cj["qSeq"] = (jobs["qSeq"] & np.uint32(0x7FFF)) | np.where(jobs["qSeq"] >> np.uint32(31), CJOB_MINUS, 0).astype(np.uint32)
+    return cj, cb, ab, anchors
+
+
+def unpack_compact(cjobs, cblocks, ab, anchors):
+    """Host restatement of the device expansion (tests): compact work-list -> (jobs, total, blocks)."""
+    n = len(cblocks)
+    size = (cblocks["size"] & CBLOCK_MAX_SIZE).astype(np.int64)
+    is_abs = (cblocks["size"] & CBLOCK_ABS) != 0
+    ix = cblocks["dt"].astype(np.int64) | (cblocks["dq"].astype(np.int64) << 16)
+    ts = np.zeros(n, dtype=np.int64); qs = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        if i % CGROUP == 0:
+            ts[i], qs[i] = anchors["tStart"][i // CGROUP], anchors["qStart"][i // CGROUP]
+        elif is_abs[i]:
+            ts[i], qs[i] = ab["tStart"][ix[i]], ab["qStart"][ix[i]]
+        else:
+            ts[i] = ts[i - 1] + size[i - 1] + int(cblocks["dt"][i]); qs[i] = qs[i - 1] + size[i - 1] + int(cblocks["dq"][i])
+    blocks = np.zeros(n, dtype=BLOCK_DTYPE)
+    blocks["tStart"] = ts; blocks["qStart"] = qs
+    blocks["size"] = size.astype(np.uint32) | np.where(cblocks["size"] & CBLOCK_JOINED, BLOCK_JOINED, 0).astype(np.uint32)
+    jobs = np.zeros(len(cjobs), dtype=JOB_DTYPE)
+    jobs["tSeq"] = cjobs["tSeq"]
+    jobs["qSeq"] = (cjobs["qSeq"] & 0x7FFF).astype(np.uint32) | np.where(cjobs["qSeq"] & CJOB_MINUS, QSEQ_MINUS, 0).astype(np.uint32)
+    jobs["firstBlock"] = cjobs["blockPtr"]; jobs["blockPtr"] = cjobs["blockPtr"]
+    jobs["clipStart"] = NO_CLIP_START; jobs["clipEnd"] = NO_CLIP_END
+    return jobs, n, blocks

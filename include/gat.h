@@ -147,6 +147,25 @@ int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl);           /* asynchronous 
 int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local);
 void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl);
 
+/* The same scoring call fed with a compact work-list: what crosses PCIe is about half of what gat_score() needs
+ * (6 bytes per block instead of 12, 8 per chain instead of 24), and a .chain file stores exactly these numbers
+ * ("size dt dq" lines, kent/src/lib/chain.c:211-227).  The device expands it into gat_job / gat_block records and then
+ * runs the kernels of gat_score().  Whole chains only (job j owns records [blockPtr[j], blockPtr[j+1]), no clip).
+ *   gat_cblock: size (<= GAT_CBLOCK_MAX_SIZE; cut longer blocks into GAT_CBLOCK_JOINED pieces) and the gap in front of
+ *               the block on both sequences.  GAT_CBLOCK_ABS: the block does not start relative to its predecessor (first
+ *               block of a chain, a gap of 65536 or more, a negative gap): dt | dq << 16 is an index into abs[].
+ *   anchors[g]: start of record 1024 * g, so that groups of 1024 records expand independently. */
+#define GAT_CBLOCK_ABS 0x8000u
+#define GAT_CBLOCK_JOINED 0x4000u
+#define GAT_CBLOCK_MAX_SIZE 0x3fffu
+#define GAT_CJOB_MINUS 0x8000u
+#define GAT_CGROUP 1024u
+typedef struct gat_cblock { uint16_t size, dt, dq; } gat_cblock;
+typedef struct gat_cjob { uint32_t blockPtr; uint16_t tSeq, qSeq; /* qSeq | GAT_CJOB_MINUS */ } gat_cjob;
+typedef struct gat_cabs { int32_t tStart, qStart; } gat_cabs;
+int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_cblock *blocks, uint64_t nBlocks,
+                      const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, int64_t *global, int64_t *local);
+
 /* Crossover points of overlapping adjacent blocks, in one batch: what kent's chainRemovePartialOverlaps asks of
  *     void cBlockFindCrossover(struct cBlock *left, struct cBlock *right, struct dnaSeq *qSeq, struct dnaSeq *tSeq,
  *                              int overlap, int matrix[256][256], int *retPos, int *retScoreAdjustment)

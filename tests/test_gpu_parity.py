@@ -361,6 +361,33 @@ def test_remove_partial_overlaps_matches_reference(kentref, tmp_path):
     assert changed > 5          # some blocks dried up and were removed
 
 
+@pytest.mark.parametrize("n_blocks,kw", [(9000, {}), (1024, dict(max_chain_blocks=5)), (3, dict(max_chain_blocks=2)),
+                                         (30000, dict(gap_mu=6.0, gap_sigma=3.0, max_gap=900000, max_len=60000, mean_log_len=5.0))])
+def test_compact_worklist_scores_like_plain(n_blocks, kw):
+    """gat_score_compact (delta-coded work-list expanded on the device) gives the scores of gat_score on the same list."""
+    from genomealignmenttools_b200.records import pack_compact, split_long_blocks
+    w, _, _ = small_world(seed=44, n_blocks=n_blocks, **kw)
+    jobs, total, blocks = split_long_blocks(w.jobs, w.total, w.blocks, 4096)
+    if n_blocks == 9000:        # out-of-order blocks inside a chain: a negative gap takes the absolute escape
+        blocks = blocks.copy()
+        i = int(jobs["firstBlock"][np.argmax(job_block_counts(jobs, total))]) + 1
+        blocks["qStart"][i + 1] = blocks["qStart"][i] - 3
+    cj, cb, ab, an = pack_compact(jobs, total, blocks)
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(Scoring(None, "medium"))
+        g, l = sc.score(jobs, total, blocks)
+        cg, cl = sc.score_compact(cj, cb, ab, an)
+        assert np.array_equal(g, cg) and np.array_equal(l, cl)
+        escapes = np.nonzero((cb["size"] & 0x8000) != 0)[0]
+        escapes = escapes[escapes % 1024 != 0]                                   # a group's first record takes its anchor
+        if len(escapes):
+            bad = cb.copy(); bad["dt"][escapes[0]] = 0xFFFF; bad["dq"][escapes[0]] = 0xFFFF      # absolute index out of range
+            with pytest.raises(GatError):
+                sc.score_compact(cj, bad, ab, an)
+            g2, l2 = sc.score_compact(cj, cb, ab, an)                            # the context survives
+            assert np.array_equal(g, g2)
+
+
 def test_resident_worklist_matches_one_shot():
     w, _, _ = small_world(seed=12, n_blocks=9000)
     with ChainScorer(0) as sc:

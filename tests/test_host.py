@@ -173,6 +173,23 @@ def test_chain_reader_pieces_parsed_concurrently_equal_sequential(golden, tmp_pa
     assert msgs[0] == msgs[1] and b"line" in msgs[0]
 
 
+def test_compact_worklist_roundtrip():
+    """records.pack_compact (6-byte delta-coded blocks + absolute table + group anchors) expands back to the very records,
+    including chain starts, gaps beyond 16 bits, negative gaps (out-of-order blocks) and JOINED pieces."""
+    from genomealignmenttools_b200.records import pack_compact, unpack_compact, split_long_blocks, CBLOCK_ABS
+    jobs, total, blocks = synth.make_chains([5_000_000, 800_000], [4_000_000, 900_000], 20000, seed=5, max_chain_blocks=3000,
+                                            max_len=30000, gap_mu=6.0, gap_sigma=3.0, max_gap=900000)
+    blocks["tStart"][100], blocks["tStart"][101] = blocks["tStart"][101], blocks["tStart"][100]      # a negative gap
+    jobs, total, blocks = split_long_blocks(jobs, total, blocks, 4096)
+    cj, cb, ab, an = pack_compact(jobs, total, blocks)
+    j2, t2, b2 = unpack_compact(cj, cb, ab, an)
+    assert np.array_equal(jobs, j2) and total == t2 and np.array_equal(blocks, b2)
+    assert len(ab) > len(jobs)                                     # escapes beyond the chain starts
+    assert (cj.nbytes + cb.nbytes + ab.nbytes + an.nbytes) < 0.6 * (jobs.nbytes + blocks.nbytes)
+    with pytest.raises(ValueError):
+        pack_compact(*synth.make_chains([5_000_000], [4_000_000], 2000, seed=6, max_len=30000, mean_log_len=9.0))   # unsplit long blocks
+
+
 def test_chain_reader_errors(tmp_path):
     lib = hostlib.load()
     good = "chain 100 chrA 1000 + 10 60 chrB 900 - 5 65 7\n20\t10\t20\n20\n\n"
