@@ -459,8 +459,8 @@ def main():
     assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "compact e2e and resident results differ"
     compact_bytes = int(cj.nbytes + cb.nbytes + ab.nbytes + an.nbytes)
     h2d_ms, kern_ms = parts_of(compact_call)
-    e2e_parts = {"h2d_and_expand_ms": round(h2d_ms, 4), "kernels_ms": round(kern_ms, 4),
-                 "d2h_and_sync_ms": round(max(0.0, e2e_ms - h2d_ms - kern_ms), 4)}
+    # (a profiled call runs unsliced on one stream; the timed calls overlap the copy of a slice with the kernels of the one before)
+    e2e_parts = {"h2d_and_expand_ms_unsliced": round(h2d_ms, 4), "kernels_ms_unsliced": round(kern_ms, 4)}
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     per_step_ms = ms / args.steps

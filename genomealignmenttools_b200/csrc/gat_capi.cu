@@ -26,6 +26,9 @@ static int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(GAT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+constexpr int COMPACT_SLICES = 4;
+static_assert(GAT_CGROUP % gat::CHUNK == 0, "a slice of record groups must be a whole number of chunks");
+
 struct GenomeDev {
     uint2 *planes = nullptr;
     uint32_t *nplane = nullptr, *nwin = nullptr;
@@ -62,6 +65,8 @@ struct gat_ctx {
     gat_worklist *scratch = nullptr;   // device buffers of gat_score(), grown on demand and reused
     void *compactBuf = nullptr;        // device staging of gat_score_compact(): jobs, blocks, abs, anchors
     size_t compactCap = 0;
+    cudaStream_t copyStream = nullptr; // gat_score_compact(): slices are copied here while earlier ones are scored
+    cudaEvent_t sliceEv[COMPACT_SLICES + 1] = {};
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
 };
@@ -135,6 +140,7 @@ extern "C" void gat_destroy(gat_ctx *ctx)
     ctx->genome[1].release();
     if (ctx->scratch) { freeWorklistBuffers(ctx->scratch); delete ctx->scratch; }
     cudaFree(ctx->compactBuf);
+    if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); for (auto &e : ctx->sliceEv) cudaEventDestroy(e); }
     cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense); cudaFree(ctx->err);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -427,6 +433,50 @@ extern "C" int gat_worklist_create(gat_ctx *ctx, const gat_job *jobs, uint64_t n
     return GAT_OK;
 }
 
+static ScoreParams scoreParams(gat_ctx *ctx, gat_worklist *wl)
+{
+    ScoreParams P;
+    P.info = wl->info; P.blocks = wl->blocks;
+    P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
+    P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks; P.headBits = wl->headBits; P.chunkBase = 0;
+    P.maxBlockBases = ctx->maxBlockBases;
+    P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
+    memcpy(P.coef, ctx->coef, sizeof P.coef);
+    P.gap = ctx->gap;
+    P.gapSmall = ctx->gapSmall; P.gapDense = ctx->gapDense; P.gapLongPos = ctx->gapLongPos; P.gapLongVal = ctx->gapLongVal;
+    P.outGlobal = wl->outGlobal; P.outLocal = wl->outLocal;
+    P.chunkHead = wl->chunkHead; P.chunkTail = wl->chunkTail; P.chunkTailJob = wl->chunkTailJob;
+    P.err = ctx->err;
+    return P;
+}
+
+// bitmap reset + jobPrepKernel: needs the jobs only, not the block records
+static int launchPrep(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
+{
+    CU(cudaMemsetAsync(wl->headBits, 0, headWords(wl->nChunks) * sizeof(uint32_t), st));
+    const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
+    unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
+    jobPrepKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
+                                        (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
+                                        wl->headBits, wl->outGlobal, wl->outLocal, ctx->err);
+    return GAT_OK;
+}
+
+// chunks [first, first + count)
+static void launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, cudaStream_t st)
+{
+    if (count == 0) return;
+    P.chunkBase = first;
+    if (ctx->sym) scoreChunksKernel<true><<<count, TPB, ctx->dynSmem, st>>>(P);
+    else scoreChunksKernel<false><<<count, TPB, ctx->dynSmem, st>>>(P);
+}
+
+static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
+{
+    fixupKernel<<<(wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
+                                                                           wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
+}
+
 extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
 {
     if (!ctx || !wl) return fail(GAT_EINVAL, "gat_worklist_run: NULL argument");
@@ -442,37 +492,15 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
         CU(cudaMemsetAsync(wl->outLocal, 0, wl->nJobs * sizeof(long long), st));
         return GAT_OK;
     }
-    ScoreParams P;
-    P.info = wl->info; P.blocks = wl->blocks;
-    P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
-    P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks; P.headBits = wl->headBits;
-    P.maxBlockBases = ctx->maxBlockBases;
-    P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
-    memcpy(P.coef, ctx->coef, sizeof P.coef);
-    P.gap = ctx->gap;
-    P.gapSmall = ctx->gapSmall; P.gapDense = ctx->gapDense; P.gapLongPos = ctx->gapLongPos; P.gapLongVal = ctx->gapLongVal;
-    P.outGlobal = wl->outGlobal; P.outLocal = wl->outLocal;
-    P.chunkHead = wl->chunkHead; P.chunkTail = wl->chunkTail; P.chunkTailJob = wl->chunkTailJob;
-    P.err = ctx->err;
-
+    ScoreParams P = scoreParams(ctx, wl);
     const bool prof = ctx->profiling;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
-    CU(cudaMemsetAsync(wl->headBits, 0, headWords(wl->nChunks) * sizeof(uint32_t), st));
-    {
-        const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
-        unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
-        jobPrepKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
-                                            (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
-                                            wl->headBits, wl->outGlobal, wl->outLocal, ctx->err);
-    }
+    int rc = launchPrep(ctx, wl, st);
+    if (rc != GAT_OK) return rc;
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-    if (ctx->sym) scoreChunksKernel<true><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
-    else scoreChunksKernel<false><<<wl->nChunks, TPB, ctx->dynSmem, st>>>(P);
+    launchScoring(ctx, P, 0, wl->nChunks, st);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
-    {
-        fixupKernel<<<(wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
-                                                     wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
-    }
+    launchFixup(ctx, wl, st);
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaGetLastError());
     ctx->stats.kernel_launches = 3;
@@ -616,28 +644,71 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                  oAnch = oAbs + up8(nAbs * sizeof(gat_cabs)), need = oAnch + up8(nGroups * sizeof(gat_cabs)) + 16;
     if (need > ctx->compactCap) {
         CU(cudaStreamSynchronize(st));
-        cudaFree(ctx->compactBuf); ctx->compactBuf = nullptr; ctx->compactCap = 0;
+        cudaFree(ctx->compactBuf);
+        ctx->compactBuf = nullptr; ctx->compactCap = 0;
         CU(cudaMalloc(&ctx->compactBuf, need + need / 8));
         ctx->compactCap = need + need / 8;
     }
     char *base = static_cast<char *>(ctx->compactBuf);
+    const gat_cjob *dJobs = reinterpret_cast<const gat_cjob *>(base + oJobs);
+    const gat_cblock *dBlocks = reinterpret_cast<const gat_cblock *>(base + oBlocks);
+    const gat_cabs *dAbs = reinterpret_cast<const gat_cabs *>(base + oAbs), *dAnch = reinterpret_cast<const gat_cabs *>(base + oAnch);
     const bool prof = ctx->profiling;
+    ctx->stats.chunks = wl->nChunks;
+    // Big lists go over in slices on a copy stream while the slices that have arrived are expanded and scored: a group
+    // of GAT_CGROUP records expands on its own and a chunk needs no record beyond its own.  (With profiling on, one
+    // slice on one stream, so that the events of gat_get_stats mean what they say.)
+    const uint64_t slices = (!prof && wl->nChunks && nBlocks >= (1u << 20)) ? COMPACT_SLICES : 1;
+    if (slices > 1 && !ctx->copyStream) {
+        CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        for (auto &e : ctx->sliceEv) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t cp = slices > 1 ? ctx->copyStream : st;
     if (prof) cudaEventRecord(ctx->ev[4], st);
-    CU(cudaMemcpyAsync(base + oJobs, jobs, nJobs * sizeof(gat_cjob), cudaMemcpyHostToDevice, st));
-    if (nBlocks) CU(cudaMemcpyAsync(base + oBlocks, blocks, nBlocks * sizeof(gat_cblock), cudaMemcpyHostToDevice, st));
-    if (nAbs) CU(cudaMemcpyAsync(base + oAbs, abs, nAbs * sizeof(gat_cabs), cudaMemcpyHostToDevice, st));
-    if (nGroups) CU(cudaMemcpyAsync(base + oAnch, anchors, nGroups * sizeof(gat_cabs), cudaMemcpyHostToDevice, st));
-    expandJobsKernel<<<(unsigned)((nJobs + 255) / 256), 256, 0, st>>>(reinterpret_cast<const gat_cjob *>(base + oJobs), nJobs, wl->jobs);
-    if (nGroups)
-        expandBlocksKernel<<<(unsigned)nGroups, CX_TPB, 0, st>>>(reinterpret_cast<const gat_cblock *>(base + oBlocks), nBlocks,
-                                                                reinterpret_cast<const gat_cabs *>(base + oAbs), nAbs,
-                                                                reinterpret_cast<const gat_cabs *>(base + oAnch), wl->blocks, ctx->err);
+    CU(cudaMemcpyAsync(base + oJobs, jobs, nJobs * sizeof(gat_cjob), cudaMemcpyHostToDevice, cp));
+    if (nAbs) CU(cudaMemcpyAsync(base + oAbs, abs, nAbs * sizeof(gat_cabs), cudaMemcpyHostToDevice, cp));
+    if (nGroups) CU(cudaMemcpyAsync(base + oAnch, anchors, nGroups * sizeof(gat_cabs), cudaMemcpyHostToDevice, cp));
+    if (slices > 1) { CU(cudaEventRecord(ctx->sliceEv[COMPACT_SLICES], cp)); CU(cudaStreamWaitEvent(st, ctx->sliceEv[COMPACT_SLICES], 0)); }
+    expandJobsKernel<<<(unsigned)((nJobs + 255) / 256), 256, 0, st>>>(dJobs, nJobs, wl->jobs);
+    ctx->stats.kernel_launches = 0;
+    if (wl->nChunks == 0) {     // every job is empty: scores are 0
+        CU(cudaMemsetAsync(wl->outGlobal, 0, nJobs * sizeof(long long), st));
+        CU(cudaMemsetAsync(wl->outLocal, 0, nJobs * sizeof(long long), st));
+    } else {
+        const ScoreParams P = scoreParams(ctx, wl);
+        if (slices == 1) {
+            CU(cudaMemcpyAsync(base + oBlocks, blocks, nBlocks * sizeof(gat_cblock), cudaMemcpyHostToDevice, st));
+            expandBlocksKernel<<<(unsigned)nGroups, CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, 0, ctx->err);
+            if (prof) CU(cudaEventRecord(ctx->ev[0], st));
+            rc = launchPrep(ctx, wl, st);
+            if (rc != GAT_OK) return rc;
+            if (prof) CU(cudaEventRecord(ctx->ev[1], st));
+            launchScoring(ctx, P, 0, wl->nChunks, st);
+            if (prof) CU(cudaEventRecord(ctx->ev[2], st));
+        } else {
+            rc = launchPrep(ctx, wl, st);
+            if (rc != GAT_OK) return rc;
+            const uint64_t groupsPerSlice = (nGroups + slices - 1) / slices;
+            for (uint64_t s = 0; s < slices; s++) {
+                const uint64_t g0 = s * groupsPerSlice, g1 = std::min<uint64_t>(nGroups, g0 + groupsPerSlice);
+                if (g0 >= g1) break;
+                const uint64_t r0 = g0 * GAT_CGROUP, r1 = std::min<uint64_t>(nBlocks, g1 * GAT_CGROUP);
+                CU(cudaMemcpyAsync(base + oBlocks + r0 * sizeof(gat_cblock), blocks + r0, (r1 - r0) * sizeof(gat_cblock), cudaMemcpyHostToDevice, cp));
+                CU(cudaEventRecord(ctx->sliceEv[s], cp));
+                CU(cudaStreamWaitEvent(st, ctx->sliceEv[s], 0));
+                expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
+                const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
+                launchScoring(ctx, P, c0, c1 - c0, st);
+            }
+        }
+        launchFixup(ctx, wl, st);
+        if (prof) CU(cudaEventRecord(ctx->ev[3], st));
+        ctx->stats.kernel_launches = 5;
+    }
     CU(cudaGetLastError());
-    rc = gat_worklist_run(ctx, wl);
-    if (rc == GAT_OK) ctx->stats.kernel_launches += 2;
-    if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[5], st);
-    if (rc == GAT_OK) rc = gat_worklist_results(ctx, wl, global, local);
-    if (rc == GAT_OK && prof) {
+    if (prof) cudaEventRecord(ctx->ev[5], st);
+    rc = gat_worklist_results(ctx, wl, global, local);
+    if (rc == GAT_OK && prof && wl->nChunks) {
         float total = 0;
         cudaEventElapsedTime(&total, ctx->ev[4], ctx->ev[0]);
         ctx->stats.h2d_ms = total;          // copies + the two expansion kernels

@@ -131,6 +131,7 @@ struct ScoreParams {
     const uint32_t *chunkJob;   // job containing the first job-block of each chunk
     const uint32_t *headBits;   // bit b: a (non-empty) job starts at job-block b; bit totalJobBlocks closes the list
     uint32_t nChunks;
+    uint32_t chunkBase;         // first chunk of this launch (gat_score_compact scores slices as their records arrive)
     uint32_t maxBlockBases;     // records longer than this are rejected (32-bit block sums)
     GenomeView t, q;
     int coef[16];               // SYM: 6 coefficients, general: 16 Moebius coefficients
@@ -537,13 +538,14 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
     __syncthreads();                    // the only CTA-wide barrier: from here on warps run on their own
     // ---- phase 0 (per warp, three independent loads): the chunk's 32 words of the job-start bitmap
     // (jobPrepKernel), the job that owns the chunk's first block, the rejection flag.
-    const uint32_t vb0 = blockIdx.x * (uint32_t)CHUNK;               // totalJobBlocks < 2^32
+    const uint32_t chunk = blockIdx.x + P.chunkBase;                 // a launch may cover a slice of the chunks
+    const uint32_t vb0 = chunk * (uint32_t)CHUNK;                    // totalJobBlocks < 2^32
     const uint32_t total = (uint32_t)P.totalJobBlocks;
     const int vEnd = (int)(total - vb0 < (uint32_t)CHUNK ? total - vb0 : (uint32_t)CHUNK);   // valid job-blocks of this chunk
     constexpr int WORDS = CHUNK / 32;   // bitmap words per chunk (<= 32: one per lane; lanes past it see the next chunk's words)
-    const uint32_t myHeadWord = __ldg(P.headBits + (size_t)blockIdx.x * WORDS + lane);
-    const uint32_t nextHead0 = __ldg(P.headBits + (size_t)(blockIdx.x + 1) * (CHUNK / 32)) & 1u;
-    const uint32_t j0 = __ldg(P.chunkJob + blockIdx.x);
+    const uint32_t myHeadWord = __ldg(P.headBits + (size_t)chunk * WORDS + lane);
+    const uint32_t nextHead0 = __ldg(P.headBits + (size_t)(chunk + 1) * (CHUNK / 32)) & 1u;
+    const uint32_t j0 = __ldg(P.chunkJob + chunk);
     if (*reinterpret_cast<volatile const int *>(P.err)) return;     // jobPrepKernel rejected the work-list (or met an empty job)
     uint32_t wrank;     // lane i: jobs that start in words 0..i-1 of the chunk, not counting the chunk's first block
     {
@@ -834,15 +836,15 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             if (ch) {
                 P.outGlobal[sWarpPendJob[w]] = fin.d;
                 P.outLocal[sWarpPendJob[w]] = finalLocal(fin);
-            } else P.chunkHead[blockIdx.x] = fin;       // job began in an earlier chunk and ends here
+            } else P.chunkHead[chunk] = fin;       // job began in an earlier chunk and ends here
         }
         if (sWarpHead[w]) { c = sWarpAgg[w]; ch = true; }
         else c = tupCombine(c, sWarpAgg[w]);
     }
     // the chunk's last valid job-block: does its job run on into the next chunk?
-    if (sLastIsEnd) P.chunkTailJob[blockIdx.x] = -1;
-    else if (ch) { P.chunkTail[blockIdx.x] = c; P.chunkTailJob[blockIdx.x] = (int)sLastJob; }
-    else { P.chunkHead[blockIdx.x] = c; P.chunkTailJob[blockIdx.x] = -1; }
+    if (sLastIsEnd) P.chunkTailJob[chunk] = -1;
+    else if (ch) { P.chunkTail[chunk] = c; P.chunkTailJob[chunk] = (int)sLastJob; }
+    else { P.chunkHead[chunk] = c; P.chunkTailJob[chunk] = -1; }
 }
 
 // ------------------------------------------------------------------ cross-chunk fix-up
@@ -1029,11 +1031,13 @@ __device__ __forceinline__ CxSeg cxCombine(const CxSeg &l, const CxSeg &r) { ret
 
 __global__ void __launch_bounds__(CX_TPB)
 expandBlocksKernel(const gat_cblock *__restrict__ cb, unsigned long long nBlocks, const gat_cabs *__restrict__ absTab,
-                   unsigned long long nAbs, const gat_cabs *__restrict__ anchors, gat_block *__restrict__ out, int *__restrict__ err)
+                   unsigned long long nAbs, const gat_cabs *__restrict__ anchors, gat_block *__restrict__ out, unsigned firstGroup,
+                   int *__restrict__ err)
 {
     __shared__ CxSeg sWarp[CX_TPB / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long g0 = (unsigned long long)blockIdx.x * GAT_CGROUP, r0 = g0 + 4ull * tid;
+    const unsigned group = blockIdx.x + firstGroup;                 // a launch may cover a slice of the groups
+    const unsigned long long g0 = (unsigned long long)group * GAT_CGROUP, r0 = g0 + 4ull * tid;
     // my four records, and the size of the record in front of them (its end is where my first step starts)
     uint32_t size[4], dt[4], dq[4];
 #pragma unroll
@@ -1051,7 +1055,7 @@ expandBlocksKernel(const gat_cblock *__restrict__ cb, unsigned long long nBlocks
     for (int k = 0; k < 4; k++) {
         CxSeg e;
         const bool first = tid == 0 && k == 0;
-        if (first) { const gat_cabs a = anchors[blockIdx.x]; e = CxSeg{a.tStart, a.qStart, true}; }
+        if (first) { const gat_cabs a = anchors[group]; e = CxSeg{a.tStart, a.qStart, true}; }
         else if (size[k] & GAT_CBLOCK_ABS) {
             const unsigned long long ix = (unsigned long long)dt[k] | ((unsigned long long)dq[k] << 16);
             if (ix < nAbs) { const gat_cabs a = absTab[ix]; e = CxSeg{a.tStart, a.qStart, true}; }
