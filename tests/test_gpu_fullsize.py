@@ -77,6 +77,23 @@ def test_config5_properties_at_10M_blocks(genomewide):
     assert np.all(l[multi] >= np.maximum(lh[0::2], gh[1::2] * 0 + 0))
 
 
+def test_config5_compact_worklist_in_slices(genomewide):
+    """gat_score_compact at 10 M blocks: the list crosses PCIe in slices that are expanded and scored while the next one is
+    copied; the scores are those of gat_score on the same (split) list."""
+    from genomealignmenttools_b200.records import pack_compact, split_long_blocks
+    sc, jobs, total, blocks = genomewide
+    sj, st, sb = split_long_blocks(jobs, total, blocks, 4096)
+    g, l = sc.score(sj, st, sb)
+    g0, l0 = sc.score(jobs, total, blocks)
+    assert np.array_equal(g, g0) and np.array_equal(l, l0)                     # JOINED pieces score like the blocks
+    cj, cb, ab, an = pack_compact(sj, st, sb)
+    assert len(cb) >= (1 << 20)                                                # enough for the sliced path
+    cg, cl = sc.score_compact(cj, cb, ab, an)
+    assert np.array_equal(g, cg) and np.array_equal(l, cl)
+    cg, cl = sc.score_compact(cj, cb, ab, an)                                  # again: buffers and streams are reused
+    assert np.array_equal(g, cg) and np.array_equal(l, cl)
+
+
 def test_config4_danrer10_chain_real_sizes(oracle, golden, tmp_path):
     """example/hg38.danRer10.chain (1 chain, 193 blocks, chr2 vs chr22 '+') with HoxD55 and loose
     gaps on synthetic .2bit at hg38 / danRer10 sizes, plus a scaled set with its block statistics."""
