@@ -67,6 +67,27 @@ extern "C" int gathost_chains_remove_partial_overlaps(gathost_chains *c, gat_ctx
           buildRecords(c->cs, c->wl); return 0;, -1)
 }
 
+struct gathost_compact { CompactWorkList cw; };
+extern "C" gathost_compact *gathost_chains_compact(const gathost_chains *c, const uint32_t *chainT, const uint32_t *chainQ)
+{
+    WorkList wl = c->wl;                 // records as built; one whole-chain job per chain
+    wl.jobs.clear(); wl.aliBases.clear(); wl.totalJobBlocks = 0;
+    gathost_compact *out = new gathost_compact();
+    try {
+        for (size_t i = 0; i < c->cs.chains.size(); i++) addChainJob(c->cs, i, chainT[i], chainQ[i], wl);
+        if (!packCompact(wl, out->cw)) { g_err = "work-list does not qualify for the compact form"; delete out; return nullptr; }
+    } catch (const Error &e) { g_err = e.message; delete out; return nullptr; }
+    return out;
+}
+extern "C" void gathost_compact_free(gathost_compact *p) { delete p; }
+extern "C" int gathost_compact_view(const gathost_compact *p, const gat_cjob **jobs, uint64_t *nJobs, const gat_cblock **blocks, uint64_t *nBlocks,
+                                    const gat_cabs **abs, uint64_t *nAbs, const gat_cabs **anchors, uint64_t *nAnchors)
+{
+    *jobs = p->cw.jobs.data(); *nJobs = p->cw.jobs.size(); *blocks = p->cw.blocks.data(); *nBlocks = p->cw.blocks.size();
+    *abs = p->cw.abs.data(); *nAbs = p->cw.abs.size(); *anchors = p->cw.anchors.data(); *nAnchors = p->cw.anchors.size();
+    return 0;
+}
+
 struct gathost_twobit { TwoBitFile tb; explicit gathost_twobit(const char *p) : tb(p) {} };
 extern "C" gathost_twobit *gathost_twobit_open(const char *path) { GUARD(return new gathost_twobit(path);, nullptr) }
 extern "C" void gathost_twobit_close(gathost_twobit *t) { delete t; }

@@ -42,6 +42,15 @@ int gathost_chains_subset(const gathost_chains *c, uint64_t ix, int subStart, in
  * Blocks, counts and bounds are rewritten in place (read them back with gathost_chains_head / _blocks). */
 int gathost_chains_remove_partial_overlaps(gathost_chains *c, gat_ctx *ctx, const uint32_t *chainT, const uint32_t *chainQ);
 
+/* The chains of the set as the compact work-list of gat_score_compact (gathost::packCompact): one whole-chain job per
+ * chain.  NULL (gathost_last_error) if the set does not qualify (a record beyond GAT_CBLOCK_MAX_SIZE cannot happen:
+ * records are cut at GAT_SPLIT_BASES; more than 32768 sequences can).  Arrays are owned by the handle. */
+typedef struct gathost_compact gathost_compact;
+gathost_compact *gathost_chains_compact(const gathost_chains *c, const uint32_t *chainT, const uint32_t *chainQ);
+void gathost_compact_free(gathost_compact *p);
+int gathost_compact_view(const gathost_compact *p, const gat_cjob **jobs, uint64_t *nJobs, const gat_cblock **blocks, uint64_t *nBlocks,
+                         const gat_cabs **abs, uint64_t *nAbs, const gat_cabs **anchors, uint64_t *nAnchors);
+
 /* .2bit container (kent/src/lib/twoBit.c:422-650). */
 typedef struct gathost_twobit gathost_twobit;
 gathost_twobit *gathost_twobit_open(const char *path);

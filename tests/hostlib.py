@@ -9,7 +9,8 @@ SYMBOLS = ["gathost_last_error", "gathost_gapcalc_open", "gathost_gapcalc_close"
            "gathost_gapcalc_fill", "gathost_scorescheme", "gathost_chains_read", "gathost_chains_close",
            "gathost_chains_count", "gathost_chains_block_count", "gathost_chains_blocks", "gathost_chains_head",
            "gathost_chains_subset", "gathost_twobit_open", "gathost_twobit_close", "gathost_twobit_count",
-           "gathost_twobit_seq", "gathost_shard_jobs", "gathost_chains_remove_partial_overlaps"]
+           "gathost_twobit_seq", "gathost_shard_jobs", "gathost_chains_remove_partial_overlaps", "gathost_chains_compact",
+           "gathost_compact_free", "gathost_compact_view"]
 _vp, _u64 = ctypes.c_void_p, ctypes.c_uint64
 
 

@@ -190,6 +190,45 @@ def test_compact_worklist_roundtrip():
         pack_compact(*synth.make_chains([5_000_000], [4_000_000], 2000, seed=6, max_len=30000, mean_log_len=9.0))   # unsplit long blocks
 
 
+def test_cpp_compact_packer_agrees_with_python(golden):
+    """gathost::packCompact (what bin/scoreChain sends to gat_score_compact) == records.pack_compact on the same chains."""
+    from genomealignmenttools_b200.records import (pack_compact, CJOB_DTYPE, CBLOCK_DTYPE, CABS_DTYPE, NO_CLIP_START, NO_CLIP_END,
+                                                   QSEQ_MINUS)
+    lib = hostlib.load()
+    path = os.path.join(golden, "synth_small", "in.chain")
+    cs = lib.gathost_chains_read(path.encode())
+    assert cs
+    heads = hostlib.chain_heads(lib, cs)
+    blocks = hostlib.chain_blocks(lib, cs)                 # device records (long blocks already cut)
+    n = len(heads)
+    ct = (np.arange(n) % 3).astype(np.uint32); cq = (np.arange(n) % 5).astype(np.uint32)
+    lib.gathost_chains_compact.restype = ctypes.c_void_p
+    lib.gathost_chains_compact.argtypes = [ctypes.c_void_p] * 3
+    h = lib.gathost_chains_compact(cs, ct.ctypes.data, cq.ctypes.data)
+    assert h, lib.gathost_last_error()
+    ptrs = [ctypes.c_void_p() for _ in range(4)]; counts = [ctypes.c_uint64() for _ in range(4)]
+    lib.gathost_compact_view.argtypes = [ctypes.c_void_p] * 9
+    args = []
+    for p_, c_ in zip(ptrs, counts):
+        args += [ctypes.byref(p_), ctypes.byref(c_)]
+    assert lib.gathost_compact_view(h, *[ctypes.cast(a, ctypes.c_void_p) for a in args]) == 0
+    got = []
+    for p_, c_, dt in zip(ptrs, counts, (CJOB_DTYPE, CBLOCK_DTYPE, CABS_DTYPE, CABS_DTYPE)):
+        k = int(c_.value)
+        buf = (ctypes.c_uint8 * (dt.itemsize * k)).from_address(p_.value) if k else b""
+        got.append(np.frombuffer(buf, dtype=dt, count=k).copy())
+    jobs = np.zeros(n, dtype=JOB_DTYPE)
+    jobs["tSeq"] = ct
+    jobs["qSeq"] = cq | np.array([QSEQ_MINUS if hd["qStrand"] == "-" else 0 for hd in heads], dtype=np.uint32)
+    jobs["firstBlock"] = [hd["firstBlock"] for hd in heads]; jobs["blockPtr"] = jobs["firstBlock"]
+    jobs["clipStart"] = NO_CLIP_START; jobs["clipEnd"] = NO_CLIP_END
+    want = pack_compact(jobs, len(blocks), blocks)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    lib.gathost_compact_free.argtypes = [ctypes.c_void_p]
+    lib.gathost_compact_free(h)
+
+
 def test_chain_reader_errors(tmp_path):
     lib = hostlib.load()
     good = "chain 100 chrA 1000 + 10 60 chrB 900 - 5 65 7\n20\t10\t20\n20\n\n"
