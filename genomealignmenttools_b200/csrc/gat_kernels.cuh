@@ -391,6 +391,7 @@ struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 #endif
 #ifndef GAT_PREFETCH
 #define GAT_PREFETCH 2      // bit 1: fetch the next sub-tile's job and record while the current one is processed
+                            // (asking L2 for a block's last sector from the descriptor pass was measured: no gain)
 #endif
 constexpr int P1_UNROLL = GAT_P1_UNROLL;   // sub-tiles of phase 1 in flight per warp
 constexpr int TILE = 32 * BPT;             // job-blocks per warp
@@ -634,12 +635,6 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             // without bases read the front padding
             const uint2 ta = __ldg(P.t.planes + tW), tb = __ldg(P.t.planes + tW + 1);
             const uint2 qa = __ldg(P.q.planes + qW), qb = __ldg(P.q.planes + qW + 1);
-#if GAT_PREFETCH & 1
-            if (n > 32) {       // the item loop reads the rest of the block soon: ask L2 for its last sector now
-                prefetchL2(P.t.planes + tW + ((tSh + n - 1) >> 5));
-                prefetchL2(P.q.planes + qW + ((qSh + n - 1) >> 5));
-            }
-#endif
             bool mayN = false;
             if (n) mayN = wordsTouchN(P.t.nwin, tW, tW + ((tSh + n - 1) >> 5)) || wordsTouchN(P.q.nwin, qW, qW + ((qSh + n - 1) >> 5));
             // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
