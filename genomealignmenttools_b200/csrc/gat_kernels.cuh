@@ -613,7 +613,9 @@ scoreChunksKernel(const __grid_constant__ ScoreParams P)
             const bool joined = (rec.size & GAT_BLOCK_JOINED) != 0;
             // is the record after mine its continuation (a long block cut by the host)?  Then the genome words behind
             // my window are the next record's: the item loop may read ahead past my end.  (Lane 31 does not know.)
-            const bool continued = __shfl_down_sync(FULL, (int)(ok && joined), 1) != 0 && lane < 31 && !isEndOfJob(hw, lane);
+            bool continued = false;
+            if (__any_sync(FULL, ok && joined))        // split blocks are rare: most sub-tiles skip this
+                continued = __shfl_down_sync(FULL, (int)(ok && joined), 1) != 0 && lane < 31 && !isEndOfJob(hw, lane);
             int ts = rec.tStart, qs = rec.qStart;
             int te = ts + (int)(rec.size & 0x7fffffffu);
             const int cut = job.clipStart > ts ? job.clipStart - ts : 0;
