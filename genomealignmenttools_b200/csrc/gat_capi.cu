@@ -689,6 +689,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
             rc = launchPrep(ctx, wl, st);
             if (rc != GAT_OK) return rc;
             const uint64_t groupsPerSlice = (nGroups + slices - 1) / slices;
+            uint32_t sliceLaunches = 0;
             for (uint64_t s = 0; s < slices; s++) {
                 const uint64_t g0 = s * groupsPerSlice, g1 = std::min<uint64_t>(nGroups, g0 + groupsPerSlice);
                 if (g0 >= g1) break;
@@ -699,11 +700,13 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                 expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
                 launchScoring(ctx, P, c0, c1 - c0, st);
+                sliceLaunches += 2;
             }
+            ctx->stats.kernel_launches = sliceLaunches - 2;
         }
         launchFixup(ctx, wl, st);
         if (prof) CU(cudaEventRecord(ctx->ev[3], st));
-        ctx->stats.kernel_launches = 5;
+        ctx->stats.kernel_launches += 5;        // expandJobs, expandBlocks, jobPrep, scoreChunks, fixup (+ 2 per further slice)
     }
     CU(cudaGetLastError());
     if (prof) cudaEventRecord(ctx->ev[5], st);
