@@ -1117,6 +1117,8 @@ struct GpuStarter::Impl {
 GpuStarter::GpuStarter(int nGpus) : impl(new Impl)
 {
     Impl *im = impl;
+    // load the kernels with the context, on this background thread, instead of at the first launch
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     im->th = std::thread([im, nGpus]() {
         try { im->gpus = new MultiGpu(nGpus); } catch (const Error &e) { im->error = e.message; }
     });
