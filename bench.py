@@ -331,21 +331,10 @@ def main():
 
     def exchange(jobs, blocks):
         """Set-up only: every rank generated one part of the chain set; swap them (NCCL all_gather of raw bytes)."""
-        cols = []
-        for arr, dtype in ((jobs, JOB_DTYPE), (blocks, BLOCK_DTYPE)):
-            raw = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).cuda()
-            n = torch.tensor([raw.numel()], dtype=torch.int64, device="cuda")
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, n)
-            sizes = [int(x.item()) for x in sizes]
-            buf = torch.zeros(max(sizes), dtype=torch.uint8, device="cuda")
-            buf[:raw.numel()] = raw
-            got = [torch.empty_like(buf) for _ in range(world)]
-            dist.all_gather(got, buf)
-            cols.append([g[:k].cpu().numpy().view(dtype).copy() for g, k in zip(got, sizes)])
-            del raw, buf, got
+        from genomealignmenttools_b200.sharding import exchange_parts
+        parts = exchange_parts(dist, world, "cuda", jobs, blocks)
         torch.cuda.empty_cache()
-        return list(zip(*cols))
+        return parts
 
     w, _ = shard_workload(build_workload(args.blocks, world, mean_log_len=args.mean_log_len, max_len=args.max_len, rank=rank,
                                          exchange=exchange if world > 1 else None), rank, world)

@@ -74,3 +74,24 @@ def gather_scores(n_jobs, idx, global_scores, local_scores, dist=None, dst=0):
     for i, gg, ll in gathered:
         g[i] = gg; l[i] = ll
     return g, l
+
+
+def exchange_parts(dist, world, device, jobs, blocks):
+    """Set-up helper of bench.py at N > 1: every rank generated one part (jobs, blocks) of a synthetic chain set; all ranks end
+    up with every part, in rank order (an all_gather of raw bytes, padded to the longest part).  `device`: where the
+    collective's tensors live ("cuda" for NCCL, "cpu" for gloo)."""
+    import torch
+    cols = []
+    for arr in (jobs, blocks):
+        dtype = arr.dtype
+        raw = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(device)
+        n = torch.tensor([raw.numel()], dtype=torch.int64, device=device)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        buf = torch.zeros(max(sizes), dtype=torch.uint8, device=device)
+        buf[:raw.numel()] = raw
+        got = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(got, buf)
+        cols.append([g[:k].cpu().numpy().view(dtype).copy() for g, k in zip(got, sizes)])
+    return list(zip(*cols))

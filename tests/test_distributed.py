@@ -55,6 +55,32 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     assert 0 < n0 < n
 
 
+def _exchange_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sizes = ([3_000_000, 1_000_000], [2_500_000, 900_000])
+    jobs, total, blocks = synth.make_chains(*sizes, 20_000 + 7_000 * rank, seed=100 + rank)      # parts of different length
+    parts = sharding.exchange_parts(dist, world, "cpu", jobs, blocks)
+    ok = len(parts) == world
+    for r, (pj, pb) in enumerate(parts):
+        wj, wt, wb = synth.make_chains(*sizes, 20_000 + 7_000 * r, seed=100 + r)
+        ok = ok and np.array_equal(pj, wj) and np.array_equal(pb, wb)
+    np.save(out % rank, np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange_of_workload_parts(tmp_path):
+    """bench.py at N > 1: each rank generates one part of the chain set and the ranks swap them."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "ok%d.npy")
+    mp.spawn(_exchange_worker, args=(2, port, out), nprocs=2, join=True)
+    assert np.load(out % 0)[0] and np.load(out % 1)[0]
+
+
 def test_assign_single_gpu_is_identity():
     jobs, total, blocks = synth.make_chains([300_000], [250_000], 5_000, seed=5)
     part, ali = sharding.assign_jobs(jobs, total, blocks, 1)
