@@ -491,6 +491,9 @@ static void ensureScored(Scorer &scorer, const std::vector<const Break *> &todo)
 
 // ---------------------------------------------------------------- the suspect loop
 static FILE *finalChainOutFile, *suspectsRemovedOutBedFile, *newChainIDDictFile, *suspectDataFilePointer;
+// -debug (chainCleaner.c:1312-1321, 1817-1823): sub-chains and a bed line for every tested suspect
+static bool debugMode = false;
+static FILE *suspectChainFile, *brokenChainLfillChainFile, *brokenChainRfillChainFile, *brokenChainfillChainFile, *suspectFillBedFile;
 static int suspectID = 0;
 static std::map<int, int> needsRescoring;
 static const std::vector<Net> *netsP;
@@ -535,7 +538,7 @@ static void writeSubChain(FILE *f, const LiveChain &c, int subStart, int subEnd,
 }
 
 // testAndRemoveSuspect, chainCleaner.c:1191-1400.  `up` / `down` may be null.
-static bool testAndRemoveSuspect(Scorer &scorer, Break &br, Break *up, Break *down, bool &breaksUpdated, bool isPair)
+static bool testAndRemoveSuspect(Scorer &scorer, Break &br, Break *up, Break *down, bool &breaksUpdated, bool isPair, const char *debugInfo)
 {
     breaksUpdated = false;
     LiveChain &breakingChain = live.at(br.parentChainId), &brokenChain = live.at(br.chainId);
@@ -570,6 +573,20 @@ static bool testAndRemoveSuspect(Scorer &scorer, Break &br, Break *up, Break *do
                 br.parentChainId, (int)breakingChainScore, br.chainId, (int)brokenChainScore, (int)suspectLocal, (int)t.fill.global,
                 (int)t.lfill.global, (int)t.rfill.global, suspectBases, br.LgapEnd - br.LgapStart, br.RgapEnd - br.RgapStart,
                 (int)t.lfill.local, (int)t.rfill.local);
+    }
+    if (debugMode) {                    // the four sub-chains carry the scores getChainScore left in them (:559-571)
+        writeSubChain(suspectChainFile, breakingChain, br.suspectStart, br.suspectEnd, t.suspect.global, breakingChain.head.id);
+        writeSubChain(brokenChainLfillChainFile, brokenChain, br.LfillStart, br.suspectEnd, t.lfill.global, brokenChain.head.id);
+        writeSubChain(brokenChainRfillChainFile, brokenChain, br.suspectStart, br.RfillEnd, t.rfill.global, brokenChain.head.id);
+        writeSubChain(brokenChainfillChainFile, brokenChain, br.LfillStart, br.RfillEnd, t.fill.global, brokenChain.head.id);
+        fprintf(suspectFillBedFile, "%s\t%d\t%d\t%s%sSuspect__score_%1.0f__Rleft_%1.2f__Rright_%1.2f\t1000\t+\t%d\t%d\t255,0,0\n", chrom, br.suspectStart,
+                br.suspectEnd, isRemoved ? "REMOVED_" : "", debugInfo, suspectLocal, ratioL, ratioR, br.suspectStart, br.suspectEnd);
+        fprintf(suspectFillBedFile, "%s\t%d\t%d\t%sFill__score_%1.0f\t1000\t+\t%d\t%d\t0,0,255\n", chrom, br.LfillStart, br.RfillEnd, debugInfo,
+                t.fill.global, br.LfillStart, br.RfillEnd);
+        fprintf(suspectFillBedFile, "%s\t%d\t%d\t%sLfill__score_%1.0f\t1000\t+\t%d\t%d\t0,125,255\n", chrom, br.LfillStart, br.suspectEnd, debugInfo,
+                t.lfill.global, br.LfillStart, br.LfillEnd);
+        fprintf(suspectFillBedFile, "%s\t%d\t%d\t%sRfill__score_%1.0f\t1000\t+\t%d\t%d\t0,125,255\n", chrom, br.suspectStart, br.RfillEnd, debugInfo,
+                t.rfill.global, br.RfillStart, br.RfillEnd);
     }
     if (!isRemoved) {
         verbose(3, "\t\t\t===> do not remove suspect from breaking chainID %d\n", breakingChain.head.id);
@@ -621,9 +638,13 @@ static void loopOverBreaks(Scorer &scorer)
     }
     for (int parent : order) {
         BreakList &list = breaksOf[parent];
+        int totalNumIteration = 0;
+        char debugInfo[64];
         for (;;) {
             for (;;) {      // single breaks until a pass updates nothing
                 bool anyUpdated = false;
+                totalNumIteration++;
+                snprintf(debugInfo, sizeof debugInfo, "SINGLE_%d", totalNumIteration);
                 {
                     std::vector<const Break *> pass;
                     for (const Break &b : list) pass.push_back(&b);
@@ -634,7 +655,7 @@ static void loopOverBreaks(Scorer &scorer)
                     auto nextIt = std::next(it);
                     Break *down = nextIt == list.end() ? nullptr : &*nextIt;
                     bool updated = false;
-                    const bool removed = testAndRemoveSuspect(scorer, *it, up, down, updated, false);
+                    const bool removed = testAndRemoveSuspect(scorer, *it, up, down, updated, false, debugInfo);
                     if (updated) anyUpdated = true;
                     if (removed) list.erase(it);
                     it = nextIt;
@@ -643,6 +664,8 @@ static void loopOverBreaks(Scorer &scorer)
             }
             bool anyPairUpdated = false;
             if (doPairs) {
+                totalNumIteration++;
+                snprintf(debugInfo, sizeof debugInfo, "PAIR_%d", totalNumIteration);
                 for (auto it = list.begin(); it != list.end() && std::next(it) != list.end();) {
                     auto downIt = std::next(it);
                     auto afterIt = std::next(downIt);
@@ -652,7 +675,7 @@ static void loopOverBreaks(Scorer &scorer)
                         Break pair = newBreak(it->depth, it->chainId, it->parentChainId, it->chrom, it->LfillStart, it->LfillEnd,
                                               downIt->RfillStart, downIt->RfillEnd, it->LgapStart, it->LgapEnd, downIt->RgapStart, downIt->RgapEnd);
                         bool updated = false;
-                        const bool removed = testAndRemoveSuspect(scorer, pair, before, after, updated, true);
+                        const bool removed = testAndRemoveSuspect(scorer, pair, before, after, updated, true, debugInfo);
                         if (updated) anyPairUpdated = true;
                         if (removed) { list.erase(it); list.erase(downIt); it = afterIt; }
                         else it = downIt;
@@ -670,6 +693,7 @@ static int toolMain(int argc, char **argv)
     Options opt;
     opt.init(&argc, argv, optionSpecs);
     if (argc != 6) usage();
+    debugMode = opt.exists("debug");     // (the reference tests its flag for the "### DEBUG mode ###" banner before reading the option, :1694/:1710: never printed)
     const char *inChainFile = argv[1], *tNibDir = argv[2], *qNibDir = argv[3], *outChainFile = argv[4], *outRemovedSuspectsFile = argv[5];
     const std::string outChainFileUnsorted = std::string(outChainFile) + ".unsorted";
     const char *inNetFile = opt.val("net", nullptr), *tSizes = opt.val("tSizes", nullptr), *qSizes = opt.val("qSizes", nullptr);
@@ -771,6 +795,9 @@ static int toolMain(int argc, char **argv)
     {
         ChainSet cs;
         readChains(inChainFile, cs);
+        FILE *interest = nullptr;
+        if (debugMode && !(interest = fopen("chainsOfInterest.chain", "w")))
+            errAbort("mustOpen: Can't open %s to write: %s", "chainsOfInterest.chain", strerror(errno));
         size_t meta = 0;
         for (size_t c = 0; c < cs.chains.size(); c++) {
             for (; meta < cs.metaLines.size() && cs.metaLineChain[meta] <= c; meta++) fprintf(finalOut, "%s\n", cs.metaLines[meta].c_str());
@@ -781,9 +808,11 @@ static int toolMain(int argc, char **argv)
                 LiveChain &lc = live[h.id];
                 lc.head = h;
                 lc.blocks.assign(cs.blocks.begin() + h.firstBlock, cs.blocks.begin() + h.firstBlock + h.nBlocks);
+                if (interest) writeChain(interest, h, cs.blocks.data());
             } else writeChain(finalOut, h, cs.blocks.data());
         }
         for (; meta < cs.metaLines.size(); meta++) fprintf(finalOut, "%s\n", cs.metaLines[meta].c_str());
+        if (interest) fclose(interest);
     }
     for (int id : chainsOfInterest.traverse())
         if (!live.count(id)) errAbort("ERROR: cannot get chain with Id %d from chainId2chain hash\n", id);
@@ -798,6 +827,14 @@ static int toolMain(int argc, char **argv)
 
     // 4. the suspect loop
     verbose(1, "4. loop over all breaks. Remove suspects if they pass our filters and write out deleted suspects to %s ...\n", outRemovedSuspectsFile);
+    if (debugMode) {                    // chainCleaner.c:1817-1823
+        auto must = [](const char *name) { FILE *f = fopen(name, "w"); if (!f) errAbort("mustOpen: Can't open %s to write: %s", name, strerror(errno)); return f; };
+        suspectChainFile = must("suspect.chain");
+        brokenChainLfillChainFile = must("brokenChainLfill.chain");
+        brokenChainRfillChainFile = must("brokenChainRfill.chain");
+        brokenChainfillChainFile = must("brokenChainfill.chain");
+        suspectFillBedFile = must("suspectsAndFills.bed");
+    }
     suspectsRemovedOutBedFile = fopen(outRemovedSuspectsFile, "w");
     if (!suspectsRemovedOutBedFile) errAbort("mustOpen: Can't open %s to write: %s", outRemovedSuspectsFile, strerror(errno));
     if (newChainIDDict && !(newChainIDDictFile = fopen(newChainIDDict, "w"))) errAbort("mustOpen: Can't open %s to write: %s", newChainIDDict, strerror(errno));
@@ -809,6 +846,10 @@ static int toolMain(int argc, char **argv)
     fclose(suspectsRemovedOutBedFile);
     if (newChainIDDictFile) fclose(newChainIDDictFile);
     if (suspectDataFilePointer) fclose(suspectDataFilePointer);
+    if (debugMode) {
+        fclose(suspectFillBedFile); fclose(suspectChainFile); fclose(brokenChainLfillChainFile); fclose(brokenChainRfillChainFile);
+        fclose(brokenChainfillChainFile);
+    }
     verbose(1, "DONE\n\n");
 
     // 5. breaking and broken chains, modified ones re-scored first (chainCleaner.c:625-644)
@@ -843,6 +884,14 @@ static int toolMain(int argc, char **argv)
     verbose(1, "DONE\n\n");
     if (scorer) verbose(2, "GPU scoring: %zu batches, %zu sub-chain jobs\n", scorer->gpuCalls, scorer->gpuJobs);
     verbose(1, "\nALL DONE. New chains are in %s. Deleted suspects in %s\n", outChainFile, outRemovedSuspectsFile);
+    if (debugMode)
+        verbose(1, "Debug mode created those output files: \n"
+                   "\tchainsOfInterest.chain     all breaking and broken chains (chain format)\n"
+                   "\tsuspect.chain              subChains of all suspects (chain format)\n"
+                   "\tbrokenChainfill.chain      subChains of all left and right parts of broken chains (chain format)\n"
+                   "\tbrokenChainLfill.chain     subChains of all left parts of broken chains (chain format)\n"
+                   "\tbrokenChainRfill.chain     subChains of all right parts of broken chains (chain format)\n"
+                   "\tsuspectsAndFills.bed       coordinates, scores and ratios of the suspects, the left/right parts of broken chains (bed9 format)\n");
     return 0;
 }
 

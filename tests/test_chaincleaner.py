@@ -72,3 +72,24 @@ def test_matches_reference_files(case, tag):
         assert sum(1 for _ in open(d / "ref.suspects.suspects.bed")) > 50
     if tag.startswith("relaxed"):
         assert sum(1 for _ in open(d / ("ref.%s.bed" % tag))) > 20
+
+
+@pytest.mark.gpu
+def test_debug_side_files_match_reference(case):
+    """-debug: chainsOfInterest.chain, the four sub-chain files and suspectsAndFills.bed (chainCleaner.c:591-616, 1312-1321),
+    written to the working directory; each side runs in a directory of its own."""
+    d = case
+    names = ["chainsOfInterest.chain", "suspect.chain", "brokenChainLfill.chain", "brokenChainRfill.chain", "brokenChainfill.chain",
+             "suspectsAndFills.bed", "out.chain", "out.bed"]
+    for side, bindir in (("ref", REFBIN), ("our", BIN)):
+        wd = d / ("debug_" + side)
+        os.makedirs(wd, exist_ok=True)
+        env = dict(os.environ, PATH=bindir + ":" + os.environ["PATH"])
+        r = subprocess.run([os.path.join(bindir, "chainCleaner"), str(d / "sorted.chain"), str(d / "t.2bit"), str(d / "q.2bit"), "out.chain", "out.bed",
+                            "-net=" + str(d / "in.net"), "-linearGap=loose", "-debug", "-minBrokenChainScore=3000", "-LRfoldThreshold=1.2", "-doPairs",
+                            "-LRfoldThresholdPairs=1.5"], cwd=wd, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.stdout == ""
+    for n in names:
+        assert filecmp.cmp(d / "debug_ref" / n, d / "debug_our" / n, shallow=False), n
+    assert sum(1 for l in open(d / "debug_ref" / "suspectsAndFills.bed") if "REMOVED_" in l) > 10
