@@ -8,6 +8,8 @@
 #include <vector>
 #include "gat.h"
 #include "gat_kernels.cuh"
+#include "gat_tiles.cuh"
+#include <stdlib.h>
 
 using namespace gat;
 
@@ -32,16 +34,17 @@ static_assert(GAT_CGROUP % gat::CHUNK == 0, "a slice of record groups must be a 
 struct GenomeDev {
     uint2 *planes = nullptr;
     uint32_t *nplane = nullptr, *nwin = nullptr;
+    uint2 *nwin2 = nullptr;
     long long *seqBase = nullptr;
     uint32_t *seqSize = nullptr;
     uint32_t nSeq = 0;
     bool loaded = false;
     void release()
     {
-        cudaFree(planes); cudaFree(nplane); cudaFree(nwin); cudaFree(seqBase); cudaFree(seqSize);
-        planes = nullptr; nplane = nwin = nullptr; seqBase = nullptr; seqSize = nullptr; nSeq = 0; loaded = false;
+        cudaFree(planes); cudaFree(nplane); cudaFree(nwin); cudaFree(nwin2); cudaFree(seqBase); cudaFree(seqSize);
+        planes = nullptr; nplane = nwin = nullptr; nwin2 = nullptr; seqBase = nullptr; seqSize = nullptr; nSeq = 0; loaded = false;
     }
-    GenomeView view() const { return GenomeView{planes, nplane, nwin, (const int64_t *)seqBase, seqSize, nSeq}; }
+    GenomeView view() const { return GenomeView{planes, nplane, nwin, nwin2, (const int64_t *)seqBase, seqSize, nSeq}; }
 };
 
 struct gat_ctx {
@@ -69,6 +72,7 @@ struct gat_ctx {
     cudaEvent_t sliceEv[COMPACT_SLICES + 1] = {};
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
+    bool oldKernel = false;            // GAT_KERNEL=chunks in the environment: the round-1 scoring kernel (A/B measurements)
 };
 
 struct gat_worklist {
@@ -81,6 +85,8 @@ struct gat_worklist {
     uint32_t *chunkJob = nullptr;
     uint32_t *headBits = nullptr;       // job-start bitmap over job-blocks (jobPrepKernel), CHUNK/32 words per chunk + slack
     bool borrowedBlocks = false;        // blocks belong to another work-list (re-run without empty jobs)
+    int plain = -1;                     // 1: whole chains tiling the record array (PLAIN kernel), 0: clips / shared records,
+                                        // -1: not known on the host, jobPrepKernel decides (both instantiations are launched)
     Tup *chunkHead = nullptr, *chunkTail = nullptr;
     int *chunkTailJob = nullptr;
     long long *outGlobal = nullptr, *outLocal = nullptr;
@@ -121,12 +127,23 @@ extern "C" int gat_create(gat_ctx **out, int device, void *stream)
         return fail(GAT_ECUDA, "gat_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
     gat_ctx *ctx = new gat_ctx();
     ctx->device = device;
-    if (stream) ctx->stream = (cudaStream_t)stream;
-    else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->ownStream = true; }
-    CU(cudaMalloc(&ctx->err, sizeof(int)));
-    CU(cudaMemset(ctx->err, 0, sizeof(int)));
-    for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
+    for (auto &ev : ctx->ev) ev = nullptr;
     memset(&ctx->stats, 0, sizeof ctx->stats);
+    const char *k = getenv("GAT_KERNEL");
+    ctx->oldKernel = k && strcmp(k, "chunks") == 0;
+    if (const char *f = getenv("GAT_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(f));   // experiment: 32 / 64 / 128
+    cudaError_t ce = cudaSuccess;
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else { ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->ownStream = ce == cudaSuccess; }
+    if (ce == cudaSuccess) ce = cudaMalloc(&ctx->err, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(ctx->err, 0, sizeof(int));
+    for (auto &ev : ctx->ev) if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
+    if (ce != cudaSuccess) {            // release whatever exists
+        const bool haveStream = ctx->stream != nullptr;
+        if (!haveStream) ctx->ownStream = false;
+        gat_destroy(ctx);
+        return fail(GAT_ECUDA, "gat_create failed: %s", cudaGetErrorString(ce));
+    }
     *out = ctx;
     return GAT_OK;
 }
@@ -135,14 +152,14 @@ extern "C" void gat_destroy(gat_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->genome[0].release();
     ctx->genome[1].release();
     if (ctx->scratch) { freeWorklistBuffers(ctx->scratch); delete ctx->scratch; }
     cudaFree(ctx->compactBuf);
     if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); for (auto &e : ctx->sliceEv) cudaEventDestroy(e); }
     cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense); cudaFree(ctx->err);
-    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -217,6 +234,7 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
     CUG(cudaMalloc(&g.planes, planeWords * 4));
     CUG(cudaMalloc(&g.nplane, nWords * 4));
     CUG(cudaMalloc(&g.nwin, winWords * 4));
+    CUG(cudaMalloc(&g.nwin2, winWords * sizeof(uint2)));
     CUG(cudaMalloc(&g.seqBase, nImages * sizeof(long long)));
     CUG(cudaMalloc(&g.seqSize, nSeq * sizeof(uint32_t)));
     CUG(cudaMalloc(&dRaw, packedBytes + 16));
@@ -248,6 +266,8 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
         revCompKernel<<<(unsigned)grid, 256, 0, st>>>(g.seqSize, g.seqBase, dWordStart, nSeq, words, g.planes, g.nplane, g.nwin);
         CUG(cudaGetLastError());
     }
+    nwinPairKernel<<<(unsigned)((winWords + 255) / 256), 256, 0, st>>>(g.nwin, winWords, g.nwin2);
+    CUG(cudaGetLastError());
     CUG(cudaStreamSynchronize(st));
 #undef CUG
     cleanup();
@@ -305,6 +325,7 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
             if (s->matrix[q][t] > (1 << 18) || s->matrix[q][t] < -(1 << 18))
                 return fail(GAT_EINVAL, "gat_set_scoring: |matrix| above 2^18 would overflow the 32-bit sums of a GAT_SPLIT_BASES record");
     CU(cudaSetDevice(ctx->device));
+    ctx->scoringSet = false;            // stays false if anything below fails: no scoring on half-built tables
     {   // block sums are 32-bit on the device: records may hold at most (2^31-1)/max|M| bases
         int maxAbs = 1;
         for (int q = 0; q < 4; q++)
@@ -379,10 +400,10 @@ static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_
         const uint64_t cc = nChunks > wl->capChunks ? nChunks + nChunks / 8 : wl->capChunks;
         freeWorklistBuffers(wl);
         CU(cudaMalloc(&wl->jobs, (cj + 1) * sizeof(gat_job)));
-        CU(cudaMalloc(&wl->info, (cj + 1) * sizeof(JobInfo)));
-        if (!wl->borrowedBlocks) CU(cudaMalloc(&wl->blocks, (cb + 1) * sizeof(gat_block)));
+        CU(cudaMalloc(&wl->info, (cj + 1 + 2 * CHUNK) * sizeof(JobInfo)));     // slack: lanes without a block read past the last job
+        if (!wl->borrowedBlocks) CU(cudaMalloc(&wl->blocks, (cb + 3) * sizeof(gat_block)));   // slack: bulk copies round up to 16 bytes
         CU(cudaMalloc(&wl->chunkJob, (cc + 1) * sizeof(uint32_t)));
-        CU(cudaMalloc(&wl->headBits, headWords(cc) * sizeof(uint32_t)));
+        CU(cudaMalloc(&wl->headBits, (headWords(cc) + 1) * sizeof(uint32_t)));     // + the mode word behind the bitmap
         CU(cudaMalloc(&wl->chunkHead, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTail, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTailJob, (cc + 1) * sizeof(int)));
@@ -426,6 +447,11 @@ extern "C" int gat_worklist_create(gat_ctx *ctx, const gat_job *jobs, uint64_t n
     CU(cudaSetDevice(ctx->device));
     gat_worklist *wl = nullptr;
     int rc = allocWorklist(ctx, nJobs, totalJobBlocks, nBlocks, &wl);
+    if (rc == GAT_OK) {     // a resident list is looked at once: whole chains tiling the record array take the PLAIN kernel
+        wl->plain = totalJobBlocks <= nBlocks ? 1 : 0;
+        for (uint64_t j = 0; j < nJobs && wl->plain; j++)
+            if (jobs[j].firstBlock != jobs[j].blockPtr || jobs[j].clipStart != GAT_NO_CLIP_START || jobs[j].clipEnd != GAT_NO_CLIP_END) wl->plain = 0;
+    }
     if (rc == GAT_OK) rc = uploadWorklist(ctx, wl, jobs, blocks);
     if (rc == GAT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(GAT_ECUDA, "work-list upload failed");
     if (rc != GAT_OK) { gat_worklist_destroy(ctx, wl); return rc; }
@@ -447,28 +473,47 @@ static ScoreParams scoreParams(gat_ctx *ctx, gat_worklist *wl)
     P.outGlobal = wl->outGlobal; P.outLocal = wl->outLocal;
     P.chunkHead = wl->chunkHead; P.chunkTail = wl->chunkTail; P.chunkTailJob = wl->chunkTailJob;
     P.err = ctx->err;
+    P.modeFlags = wl->plain < 0 ? reinterpret_cast<const int *>(wl->headBits + headWords(wl->nChunks)) : nullptr;
     return P;
 }
 
 // bitmap reset + jobPrepKernel: needs the jobs only, not the block records
 static int launchPrep(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 {
-    CU(cudaMemsetAsync(wl->headBits, 0, headWords(wl->nChunks) * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(wl->headBits, 0, (headWords(wl->nChunks) + 1) * sizeof(uint32_t), st));
     const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
     unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
     jobPrepKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
                                         (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
-                                        wl->headBits, wl->outGlobal, wl->outLocal, ctx->err);
+                                        wl->headBits, reinterpret_cast<int *>(wl->headBits + headWords(wl->nChunks)),
+                                        wl->outGlobal, wl->outLocal, ctx->err);
     return GAT_OK;
 }
 
 // chunks [first, first + count)
-static void launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, cudaStream_t st)
+// `plain`: 1 / 0 = the list's mode as the host knows it, -1 = jobPrepKernel's verdict decides on the device: both
+// instantiations are launched and the one that does not apply returns at once.
+static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, cudaStream_t st)
 {
-    if (count == 0) return;
+    if (count == 0) return 0;
     P.chunkBase = first;
-    if (ctx->sym) scoreChunksKernel<true><<<count, TPB, ctx->dynSmem, st>>>(P);
-    else scoreChunksKernel<false><<<count, TPB, ctx->dynSmem, st>>>(P);
+    if (ctx->oldKernel) {
+        if (ctx->sym) scoreChunksKernel<true><<<count, TPB, ctx->dynSmem, st>>>(P);
+        else scoreChunksKernel<false><<<count, TPB, ctx->dynSmem, st>>>(P);
+        return 1;
+    }
+    int launches = 0;
+    if (plain != 0) {
+        if (ctx->sym) scoreTilesKernel<true, true><<<count, TPB, 0, st>>>(P);
+        else scoreTilesKernel<false, true><<<count, TPB, 0, st>>>(P);
+        launches++;
+    }
+    if (plain <= 0) {
+        if (ctx->sym) scoreTilesKernel<true, false><<<count, TPB, 0, st>>>(P);
+        else scoreTilesKernel<false, false><<<count, TPB, 0, st>>>(P);
+        launches++;
+    }
+    return launches;
 }
 
 static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
@@ -498,12 +543,12 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     int rc = launchPrep(ctx, wl, st);
     if (rc != GAT_OK) return rc;
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-    launchScoring(ctx, P, 0, wl->nChunks, st);
+    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, st);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     launchFixup(ctx, wl, st);
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaGetLastError());
-    ctx->stats.kernel_launches = 3;
+    ctx->stats.kernel_launches = 2 + scoreLaunches;
     return GAT_OK;
 }
 
@@ -551,6 +596,7 @@ static int rerunWithoutEmptyJobs(gat_ctx *ctx, gat_worklist *wl, int64_t *global
     }
     gat_worklist tmp;
     tmp.borrowedBlocks = true;
+    tmp.plain = -1;
     int rc = shapeWorklist(ctx, &tmp, kept.size(), wl->totalJobBlocks, wl->nBlocks);
     tmp.blocks = wl->blocks;
     std::vector<int64_t> g(kept.size()), l(kept.size());
@@ -606,6 +652,7 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
     if (!ctx->scratch) ctx->scratch = new gat_worklist();
     gat_worklist *wl = ctx->scratch;
     int rc = shapeWorklist(ctx, wl, nJobs, totalJobBlocks, nBlocks);
+    wl->plain = -1;
     cudaStream_t st = ctx->stream;
     const bool prof = ctx->profiling;
     if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[4], st);
@@ -637,6 +684,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     gat_worklist *wl = ctx->scratch;
     int rc = shapeWorklist(ctx, wl, nJobs, nBlocks, nBlocks);
     if (rc != GAT_OK) return rc;
+    wl->plain = 1;              // whole chains by construction
     cudaStream_t st = ctx->stream;
     const uint64_t nGroups = (nBlocks + GAT_CGROUP - 1) / GAT_CGROUP;
     auto up8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
@@ -683,7 +731,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
             rc = launchPrep(ctx, wl, st);
             if (rc != GAT_OK) return rc;
             if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-            launchScoring(ctx, P, 0, wl->nChunks, st);
+            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, st);
             if (prof) CU(cudaEventRecord(ctx->ev[2], st));
         } else {
             rc = launchPrep(ctx, wl, st);
@@ -699,7 +747,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                 CU(cudaStreamWaitEvent(st, ctx->sliceEv[s], 0));
                 expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
-                launchScoring(ctx, P, c0, c1 - c0, st);
+                launchScoring(ctx, P, c0, c1 - c0, wl->plain, st);
                 sliceLaunches += 2;
             }
             ctx->stats.kernel_launches = sliceLaunches - 2;

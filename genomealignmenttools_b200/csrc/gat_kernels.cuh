@@ -46,7 +46,8 @@ constexpr int ERR_EMPTYJOB = 32;   // not an error: a job without blocks; the ho
 struct GenomeView {
     const uint2 *planes;      // word n = {high bits, low bits} of bases [32n, 32n+32)
     const uint32_t *nplane;   // word n = N bits of bases [32n, 32n+32)
-    const uint32_t *nwin;     // bit w = window w (1024 bases) contains an N
+    const uint32_t *nwin;     // bit w = window w (256 bases) contains an N
+    const uint2 *nwin2;       // nwin2[i] = {nwin[i], nwin[i + 1]}: one aligned load covers the 32 windows from any window on
     const int64_t *seqBase;   // first base of each sequence in the padded coordinate (multiple of 128)
     const uint32_t *seqSize;
     uint32_t nSeq;
@@ -144,6 +145,7 @@ struct ScoreParams {
     Tup *chunkHead, *chunkTail;
     int *chunkTailJob;
     int *err;
+    const int *modeFlags;       // verdicts of jobPrepKernel about the whole list (MODE_*); NULL: the host knows the mode
 };
 
 // ------------------------------------------------------------------ gap cost
@@ -323,7 +325,7 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
                               const int64_t *__restrict__ tSeqBase, const uint32_t *__restrict__ tSeqSize, uint32_t tNSeq,
                               const int64_t *__restrict__ qSeqBase, const uint32_t *__restrict__ qSeqSize, uint32_t qNSeq,
                               JobInfo *__restrict__ info, uint32_t *__restrict__ chunkJob, uint32_t nChunks,
-                              uint32_t *__restrict__ headBits,
+                              uint32_t *__restrict__ headBits, int *__restrict__ modeFlags,
                               long long *__restrict__ outGlobal, long long *__restrict__ outLocal, int *__restrict__ err)
 {
     const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -331,8 +333,10 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
     o.tBaseW = o.qBaseW = o.tSize = o.qSize = 0; o.clipStart = o.clipEnd = 0; o.delta = 0;
     o.blockPtr = (uint32_t)total;                       // sentinel record nJobs closes the CSR
     unsigned long long c0 = 0, c1 = 0;                  // chunks [c0, c1) start inside this job
+    bool general = false;                               // clips, or does not start at its own blockPtr
     if (j < nJobs) {
         const gat_job job = loadJob(jobs, (uint32_t)j);
+        general = job.firstBlock != job.blockPtr || job.clipStart != GAT_NO_CLIP_START || job.clipEnd != GAT_NO_CLIP_END;
         const unsigned long long bp = job.blockPtr;
         const unsigned long long np = (j + 1 < nJobs) ? (unsigned long long)__ldg(&jobs[j + 1].blockPtr) : total;
         int e = 0;
@@ -359,8 +363,9 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
             if (c1 > nChunks) c1 = nChunks;
         }
     }
-    // chunkJob: a job that covers a few chunk boundaries writes them itself, the warp shares the long ones
     const unsigned lane = threadIdx.x & 31;
+    if (__any_sync(FULL, general) && lane == 0) atomicOr(modeFlags, 1 /* MODE_GENERAL */);
+    // chunkJob: a job that covers a few chunk boundaries writes them itself, the warp shares the long ones
     const bool wide = c1 > c0 + 4;
     if (!wide) for (unsigned long long c = c0; c < c1; c++) chunkJob[c] = (uint32_t)j;
     for (unsigned m = __ballot_sync(FULL, wide); m; m &= m - 1) {
@@ -381,7 +386,7 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
 struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
 
 #ifndef GAT_MIN_CTAS
-#define GAT_MIN_CTAS 16
+#define GAT_MIN_CTAS 14
 #endif
 #ifndef GAT_P1_UNROLL
 #define GAT_P1_UNROLL 1
