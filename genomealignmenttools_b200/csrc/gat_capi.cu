@@ -72,6 +72,7 @@ struct gat_ctx {
     cudaEvent_t sliceEv[COMPACT_SLICES + 1] = {};
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
+    uint32_t smallBases = 1;
     bool oldKernel = false;            // GAT_KERNEL=chunks in the environment: the round-1 scoring kernel (A/B measurements)
 };
 
@@ -332,6 +333,7 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
             for (int t = 0; t < 4; t++) { const int a = s->matrix[q][t] < 0 ? -s->matrix[q][t] : s->matrix[q][t]; if (a > maxAbs) maxAbs = a; }
         const uint32_t lim = (uint32_t)(0x7fffffff / maxAbs);
         ctx->maxBlockBases = lim < GAT_MAX_BLOCK_BASES ? lim : GAT_MAX_BLOCK_BASES;
+        ctx->smallBases = (uint32_t)((1 << 19) / maxAbs);
     }
     ctx->sym = symmetricCoefs(s->matrix, ctx->coef);
     if (!ctx->sym) moebiusCoefs(s->matrix, ctx->coef);
@@ -465,7 +467,7 @@ static ScoreParams scoreParams(gat_ctx *ctx, gat_worklist *wl)
     P.info = wl->info; P.blocks = wl->blocks;
     P.nJobs = wl->nJobs; P.totalJobBlocks = wl->totalJobBlocks; P.nBlocks = wl->nBlocks;
     P.chunkJob = wl->chunkJob; P.nChunks = wl->nChunks; P.headBits = wl->headBits; P.chunkBase = 0;
-    P.maxBlockBases = ctx->maxBlockBases;
+    P.maxBlockBases = ctx->maxBlockBases; P.smallBases = ctx->smallBases;
     P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
     memcpy(P.coef, ctx->coef, sizeof P.coef);
     P.gap = ctx->gap;

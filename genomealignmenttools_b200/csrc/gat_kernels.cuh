@@ -134,6 +134,7 @@ struct ScoreParams {
     uint32_t nChunks;
     uint32_t chunkBase;         // first chunk of this launch (gat_score_compact scores slices as their records arrive)
     uint32_t maxBlockBases;     // records longer than this are rejected (32-bit block sums)
+    uint32_t smallBases;        // a block of up to this many bases scores below 2^19 in absolute value (32-bit job tuples)
     GenomeView t, q;
     int coef[16];               // SYM: 6 coefficients, general: 16 Moebius coefficients
     GapView gap;

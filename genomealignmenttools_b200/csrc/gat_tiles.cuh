@@ -192,6 +192,80 @@ __device__ __noinline__ int gapCostBeyond(const ScoreParams &P, int dq, int dt)
     return gapCostExact(P.gap, P.gapSmall, P.gapLongPos, P.gapLongVal, dt == 0 ? 0 : (dq == 0 ? 1 : 2), (int)v);
 }
 
+// Phase 3 of scoreTilesKernel in 32 bits, for tiles whose block scores and gap costs all stay below 2^19 (every partial
+// sum of the tile then stays below 2^27).  Lane l holds job-blocks 4l..4l+3 of the tile: scores a4, gap costs g4 (the gap
+// BEFORE the block; 0 for a job's first block and for continuations), flags fl4 (one byte each; a position without a
+// block has flags 0, score 0, gap 0 and passes through as a continuation).  Job scores are the max-plus tuples of Tup
+// (gat_kernels.cuh), reduced in order: four blocks per lane, then one segmented warp scan in which "the nearest lane at
+// or below me whose blocks contain a job start" comes from a ballot, so only the four tuple words are shuffled.
+__device__ __forceinline__ void warpJobReduce32(const ScoreParams &P, const uint4 a4, const uint4 g4, const uint32_t fl4,
+                                                const uint32_t myWr, const uint32_t myHw, const int lane, const uint32_t leMask,
+                                                const int lastIdx, Tup *warpAgg, Tup *warpPend, int *warpHead, int *warpPendJob,
+                                                int *sLastIsEnd, uint32_t *sLastJob)
+{
+    constexpr int NEGI = -(1 << 29);
+    const int a[BPT] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
+    const int g[BPT] = {(int)g4.x, (int)g4.y, (int)g4.z, (int)g4.w};
+    int d = 0, c = NEGI, e = NEGI, f = NEGI;      // the open job at the end of my blocks so far (since its start, or since my first block)
+    bool seenHead = false, pend = false;          // pend: a job that started in front of my blocks ends inside them
+    int pd = 0, pc = NEGI, pe = NEGI, pf = NEGI;
+    uint32_t pendJob = 0;
+    uint32_t job = myWr + __popc(myHw & (0xffffffffu >> (31 - ((4 * lane) & 31))));     // job of my first block
+#pragma unroll
+    for (int k = 0; k < BPT; k++) {
+        const uint32_t fl = fl4 >> (8 * k);
+        const bool head = (fl & 1u) != 0, end = (fl & 2u) != 0, plain = (fl & 12u) == 8u;     // plain: a block that opens with a gap
+        if (k > 0) job += fl & 1u;
+        const int av = a[k], dY = av - g[k];
+        if (head) { d = 0; c = NEGI; e = NEGI; f = NEGI; seenHead = true; }
+        // a gapped block: peak test of the block in front, gap, clamp at 0, add (scoreChain.c:181-195); else: plain add
+        const int te = max(e, d), tf = max(f, c), tc = max(av, c + dY);
+        e = plain && !head ? te : e;
+        f = plain && !head ? tf : f;
+        c = plain && !head ? tc : c + av;
+        d += dY;
+        if (end) {
+            if (seenHead) {             // the job lies inside my blocks: done
+                P.outGlobal[job] = (long long)d;
+                P.outLocal[job] = (long long)max(max(0, max(c, d)), max(e, f));
+            } else { pend = true; pd = d; pc = c; pe = e; pf = f; pendJob = job; }
+        }
+    }
+    // the chunk's last job-block: does its job run on into the next chunk?  (the fix-up kernel wants to know)
+    if ((lastIdx >> 2) == lane && lastIdx >= 0) {
+        *sLastIsEnd = ((fl4 >> (8 * (lastIdx & 3))) & 2u) != 0;
+        *sLastJob = myWr + __popc(myHw & (0xffffffffu >> (31 - (lastIdx & 31))));
+    }
+    // segmented inclusive scan over the lanes: lane i takes in lanes down to the nearest one whose blocks contain a job start
+    const uint32_t headMask = __ballot_sync(FULL, seenHead);
+    const uint32_t below = headMask & leMask;
+    const int dist = below ? __clz(below) - (31 - lane) : lane;       // lanes I may take in
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int od = __shfl_up_sync(FULL, d, off), oc = __shfl_up_sync(FULL, c, off);
+        const int oe = __shfl_up_sync(FULL, e, off), of = __shfl_up_sync(FULL, f, off);
+        if (off <= dist) {              // (od, oc, oe, of) first, then mine
+            const int nf = max(max(of, f), oc + e), ne = max(oe, od + e), nc = max(c, oc + d);
+            f = nf; e = ne; c = nc; d += od;
+        }
+    }
+    int cd = __shfl_up_sync(FULL, d, 1), cc = __shfl_up_sync(FULL, c, 1), ce = __shfl_up_sync(FULL, e, 1), cf = __shfl_up_sync(FULL, f, 1);
+    if (lane == 0) { cd = 0; cc = NEGI; ce = NEGI; cf = NEGI; }
+    const bool carryHead = (headMask & (leMask >> 1)) != 0;     // the job that runs into my blocks started inside this warp
+    if (pend) {
+        const TupT<int> fin{cd + pd, max(pc, cc + pd), max(ce, cd + pe), max(max(cf, pf), cc + pe)};
+        if (carryHead) {
+            P.outGlobal[pendJob] = (long long)fin.d;
+            P.outLocal[pendJob] = finalLocal(fin);
+        } else { *warpPend = tWiden<int>(fin); *warpPendJob = (int)pendJob; }     // it started before this warp: at most one such lane
+    }
+    const bool anyCross = __any_sync(FULL, pend && !carryHead);
+    if (lane == 31) {
+        *warpAgg = tWiden<int>(TupT<int>{d, c, e, f}); *warpHead = headMask != 0;
+        if (!anyCross) *warpPendJob = -1;
+    }
+}
+
 template <bool SYM, bool PLAIN>
 __global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
 scoreTilesKernel(const __grid_constant__ ScoreParams P)
@@ -296,7 +370,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
     // sub-tiles are interleaved (front 0, front 1, back 0, front 2, back 1, ...), so two sub-tiles' loads are in flight per
     // warp and the shuffle chain of the list prefix runs under the memory latency.  The four sub-tiles are unrolled: every
     // shared-memory offset is an immediate.
-    uint32_t seen = 0;                  // 1: some block of mine may contain N, 2: some block is worth reading ahead for
+    uint32_t seen = 0;                  // 1: some block of mine may contain N, 2: some block of mine is big (see back())
     int nSlots = 0;                     // blocks of this tile with more than 32 bases: they get a slot in the item list
     uint32_t itemBase = 0;              // items of the list so far
     const uint2 *__restrict__ tPlanes = P.t.planes, *__restrict__ qPlanes = P.q.planes;
@@ -404,7 +478,8 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             sts(outA + SM_SCORE + 128u * sub, (uint32_t)scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, __popc(vmask)));
             sts(outA + SM_GAP + 128u * sub, (uint32_t)F.gap);
             sts8(flagA + 32u * sub, (F.misc >> 16) | (mayN ? 16u : 0u));
-            seen |= (mayN ? 1u : 0u) | (n > 1024u * GAT_AHEAD ? 2u : 0u);
+            // 2: the block's score or gap cost may reach 2^19: this tile's jobs are reduced in 64 bits
+            seen |= (mayN ? 1u : 0u) | ((n > P.smallBases) | ((uint32_t)(F.gap + (1 << 19)) >= (1u << 20)) ? 2u : 0u);
         };
 
 #if GAT_INTERLEAVE
@@ -423,7 +498,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         { const Front F = front(IntC<3>()); back(IntC<3>(), F); }
 #endif
     }
-    const bool anyN = __any_sync(FULL, (seen & 1u) != 0u), anyLong = __any_sync(FULL, (seen & 2u) != 0u);
+    const bool anyN = __any_sync(FULL, (seen & 1u) != 0u), small = !__any_sync(FULL, (seen & 2u) != 0u);
     __syncwarp();
 
     // ---- phase 2: the item list, 32 items per round, adjacent lanes = adjacent words of a block (coalesced).  The slots
@@ -451,9 +526,6 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             const uint2 *tp = tPlanes + (sl.x + i);                                                         \
             const uint2 *qp = qPlanes + (sl.y + i);                                                         \
             W0 = ldgPair(tp); W1 = ldgPair(tp + 1); W2 = ldgPair(qp); W3 = ldgPair(qp + 1);                         \
-            if (GAT_AHEAD && anyLong) {         /* inside a long block: ask L2 for the words GAT_AHEAD rounds from now */ \
-                if (LEFT > 1024 * GAT_AHEAD) { prefetchL2(tp + 32 * GAT_AHEAD); prefetchL2(qp + 32 * GAT_AHEAD); } \
-            }                                                                                               \
         }
 #define GAT_CONSUME(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                      \
         {                                                                                                   \
@@ -501,18 +573,17 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         const uint4 a4 = lds128(sm + SM_SCORE + 16u * (uint32_t)lane);
         const uint4 g4 = lds128(sm + SM_GAP + 16u * (uint32_t)lane);
         const uint32_t fl4 = lds(sm + SM_FLAG + 4u * (uint32_t)lane);
-        const int a[BPT] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
-        const int g[BPT] = {(int)g4.x, (int)g4.y, (int)g4.z, (int)g4.w};
-        long long mag = 0;
-#pragma unroll
-        for (int k = 0; k < BPT; k++) mag += (long long)(a[k] < 0 ? -(long long)a[k] : (long long)a[k]) + (g[k] < 0 ? -(long long)g[k] : (long long)g[k]);
-        const bool small = __all_sync(FULL, mag < (1LL << 22));
         // bitmap word of my four blocks and the job rank in front of it (job = rank + popc(word & lanes up to the block))
         const uint32_t myWr = lds(sm + SM_RANK + 4u * (uint32_t)(lane >> 3)), myHw = lds(sm + SM_HEAD + 4u * (uint32_t)(lane >> 3));
-        if (small) warpJobReduce<int>(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
-                                      sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
-        else warpJobReduceWide(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
-                               sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
+        if (small) {
+            warpJobReduce32(P, a4, g4, fl4, myWr, myHw, lane, leMask, vEnd - 1 - warpV0,
+                            &sWarpAgg[warp], &sWarpPend[warp], &sWarpHead[warp], &sWarpPendJob[warp], &sLastIsEnd, &sLastJob);
+        } else {
+            const int a[BPT] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
+            const int g[BPT] = {(int)g4.x, (int)g4.y, (int)g4.z, (int)g4.w};
+            warpJobReduceWide(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
+                              sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
+        }
     }
     // last warp of the CTA to get here stitches the warps together
     __threadfence_block();
