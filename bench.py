@@ -7,11 +7,14 @@ synthetic hg38 x mm10 chain set -- all 455 / 66 sequences of example/{hg38,mm10}
 with the default matrix and -linearGap=medium (global + local score per chain, as scoreChain does).
 
 A step = one pass of the hot path over the rank's whole work-list.  `value` times the kernels with
-the work-list resident in HBM; `e2e` times the public call gat_score() with pinned HOST buffers
-(H2D of the work-list + kernels + D2H of the scores) every step.  Ranks are independent shards
-(weak scaling, no collective on the data path); time is the max over ranks.
+the work-list resident in HBM; `e2e` times the public call gat_score_compact() with pinned HOST buffers
+(H2D of the work-list + kernels + D2H of the scores) every step.  At N > 1 the SAME ~10 M-block set is cut
+N ways (strong scaling, the default): chains above 1/(4N) of the aligned bases are cut at block boundaries
+ and the pieces are balanced over the GPUs by greedy aligned-base load; every GPU holds a full
+genome copy and there is no collective on the data path; time is the max over ranks.  `--scaling weak` scores
+N x 10 M blocks instead (round 1's measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--blocks B] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--blocks B] [--scaling strong|weak] [--impl reference]
 """
 import argparse
 import json
@@ -78,17 +81,49 @@ def build_workload(blocks_per_gpu, world=1, plant=True, mean_log_len=3.6, max_le
 
 
 def shard_workload(w, rank, world):
-    """This rank's share: greedy aligned-base balance over the GPUs, records compacted per shard."""
+    """This rank's share: chains above 1/(4 world) of the aligned bases are cut into pieces, the pieces
+    are balanced over the GPUs by greedy aligned-base load, records are compacted per shard.  Returns the shard, the
+    indices of its jobs among the pieces, and the split (piece jobs, origin, first piece per job)."""
     from genomealignmenttools_b200 import sharding, synth
     if world == 1:
-        return w, np.arange(len(w.jobs))
-    part, _ = sharding.assign_jobs(w.jobs, w.total, w.blocks, world)
-    idx, shard, shard_total = sharding.take_shard(w.jobs, w.total, part, rank)
+        return w, np.arange(len(w.jobs)), None
+    pieces, origin, first_piece = sharding.split_giant_jobs(w.jobs, w.total, w.blocks, world)
+    part, _ = sharding.assign_jobs(pieces, w.total, w.blocks, world)
+    idx, shard, shard_total = sharding.take_shard(pieces, w.total, part, rank)
     sj, sb = sharding.compact_blocks(shard, shard_total, w.blocks)
     mine = synth.Workload(w.t, w.q, sj, shard_total, sb)
     mine.t_names, mine.q_names = w.t_names, w.q_names
-    log("[rank %d] shard: %d chains, %d blocks, %.1f Mbp aligned" % (rank, len(sj), shard_total, mine.aligned_bp / 1e6))
-    return mine, idx
+    cut = np.diff(first_piece) > 1
+    log("[rank %d] shard: %d jobs (%d pieces of the %d cut chains), %d blocks, %.1f Mbp aligned"
+        % (rank, len(sj), int(cut[origin[idx]].sum()), int(cut.sum()), shard_total, mine.aligned_bp / 1e6))
+    return mine, idx, (pieces, origin, first_piece)
+
+
+def h2d_ceiling(torch, device, barrier, nbytes=256 << 20, reps=5):
+    """This rank's pinned host -> device copy rate while every rank copies at once (GB/s): what bounds `e2e`."""
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+def source_hash():
+    """Hash of the kernel sources: a DRAM-traffic figure measured under ncu (profiles/traffic.json, written by
+    tools/measure_traffic.sh) is only quoted for the code it was measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("gat_tiles.cuh", "gat_kernels.cuh", "gat_capi.cu"):
+        h.update(open(os.path.join(ROOT, "genomealignmenttools_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # --------------------------------------------------------------------------- clocks
@@ -278,6 +313,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--blocks", type=int, default=10_000_000, help="job-blocks per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the same --blocks set cut N ways (default), weak = N x --blocks")
     ap.add_argument("--cpu-sample-mbp", type=float, default=160.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mean-log-len", type=float, default=3.6, help="block length ~ lognormal(mu, 1.1); 3.6 = the benchmark (mean 67 bp)")
@@ -293,7 +330,11 @@ def main():
     config = {"workload": "genome-wide synthetic hg38 x mm10 chain set (BASELINE.json configs[4]): all sequences of "
                           "example/{hg38,mm10}.chrom.sizes, %d job-blocks per GPU, default matrix, linearGap medium, "
                           "global+local score per chain" % args.blocks,
-              "blocks_per_gpu": args.blocks, "parallelism": "x%d GPUs: one job of %d x blocks_per_gpu job-blocks cut by greedy aligned-base balance, full genome copy per GPU, no collective" % (world, world),
+              "blocks_per_gpu": args.blocks if (world == 1 or args.scaling == "weak") else args.blocks // world,
+              "total_blocks": args.blocks * (world if args.scaling == "weak" else 1),
+              "parallelism": ("x%d GPUs, %s scaling: one set of %d job-blocks, chains above 1/(4N) of the aligned bases cut at block "
+                              "boundaries, pieces balanced by greedy aligned-base load, full genome copy per GPU, no collective"
+                              % (world, args.scaling if world > 1 else "single GPU", args.blocks * (world if args.scaling == "weak" else 1))),
               "l2": "inputs (work-list + touched genome sectors, ~0.6 GB) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -305,7 +346,7 @@ def main():
         w = build_workload(args.blocks, 1, plant=True)
         res = cpu_reference(w, args.steps, args.warmup, int(args.cpu_sample_mbp * 1e6))
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -336,8 +377,14 @@ def main():
         torch.cuda.empty_cache()
         return parts
 
-    w, _ = shard_workload(build_workload(args.blocks, world, mean_log_len=args.mean_log_len, max_len=args.max_len, rank=rank,
-                                         exchange=exchange if world > 1 else None), rank, world)
+    weak = world > 1 and args.scaling == "weak"
+    whole = build_workload(args.blocks, world if weak else 1, mean_log_len=args.mean_log_len, max_len=args.max_len, rank=rank,
+                           exchange=exchange if weak else None)
+    w, shard_idx, split = shard_workload(whole, rank, world)
+    part_local = np.zeros(0, dtype=np.uint32)     # jobs of my shard that are pieces of a cut chain: their tuples are wanted
+    if split is not None:
+        cut = np.diff(split[2]) > 1
+        part_local = np.nonzero(cut[split[1][shard_idx]])[0].astype(np.uint32)
     if args.split:
         from genomealignmenttools_b200.records import split_long_blocks
         bp = w.aligned_bp
@@ -377,8 +424,12 @@ def main():
     barrier()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
-    g_res, l_res = wl.results()
     launches = sc.stats()["kernel_launches"] * args.steps
+    part_tuples = sc.request_tuples(part_local) if len(part_local) else None      # (one more, untimed pass when pieces are present)
+    if part_tuples is not None:
+        wl.run()
+    g_res, l_res = wl.results()
+    part_tuples = part_tuples.copy() if part_tuples is not None else None
 
     # ---- kernel-only pass for the roofline (events around the scoring kernel, same stream)
     sc.set_profiling(True)
@@ -443,23 +494,59 @@ def main():
     for pin, a in zip(pins, (cj, cb, ab, an)):
         pin.array[:] = a
     pg.array[:] = 0; pl.array[:] = 0
-    compact_call = lambda: sc.score_compact(pins[0].array, pins[1].array, pins[2].array, pins[3].array, pg.array, pl.array)
+    e2e_tuples = [None]
+
+    def compact_call():
+        if len(part_local):
+            e2e_tuples[0] = sc.request_tuples(part_local)
+        sc.score_compact(pins[0].array, pins[1].array, pins[2].array, pins[3].array, pg.array, pl.array)
+
     e2e_ms = time_calls(compact_call)
     assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "compact e2e and resident results differ"
+    assert part_tuples is None or np.array_equal(e2e_tuples[0], part_tuples), "compact e2e and resident tuples differ"
     compact_bytes = int(cj.nbytes + cb.nbytes + ab.nbytes + an.nbytes)
     h2d_ms, kern_ms = parts_of(compact_call)
     # (a profiled call runs unsliced on one stream; the timed calls overlap the copy of a slice with the kernels of the one before)
     e2e_parts = {"h2d_and_expand_ms_unsliced": round(h2d_ms, 4), "kernels_ms_unsliced": round(kern_ms, 4)}
     clocks = sampler.stop(t_begin, t_end) if sampler else None
+    ceiling = h2d_ceiling(torch, torch.device("cuda", local_rank), barrier)
+
+    # ---- N > 1: rank 0 joins the pieces of the cut chains and checks every score against one GPU scoring the whole set
+    scaling_check = None
+    if world > 1 and split is not None:
+        from genomealignmenttools_b200 import sharding
+        payload = (shard_idx, g_res, l_res, shard_idx[part_local], part_tuples)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(payload, gathered, dst=0)
+        if rank == 0:
+            pieces, origin, first_piece = split
+            pg_all = np.zeros(len(pieces), dtype=np.int64); pl_all = np.zeros(len(pieces), dtype=np.int64)
+            tuples = {}
+            for idx, gg, ll, pidx, ptup in gathered:
+                pg_all[idx] = gg; pl_all[idx] = ll
+                for k, pi in enumerate(pidx):
+                    tuples[int(pi)] = ptup[k]
+            scoring = Scoring(None, "medium")
+            jg, jl = sharding.join_pieces(whole.jobs, whole.total, whole.blocks, pieces, origin, first_piece, pg_all, pl_all, tuples,
+                                          scoring.gap.cost)
+            one_g, one_l = sc.score(whole.jobs, whole.total, whole.blocks)
+            scaling_check = {"jobs": int(len(jg)), "cut_chains": int((np.diff(first_piece) > 1).sum()),
+                             "pieces": int(len(pieces) - len(jg) + (np.diff(first_piece) > 1).sum()),
+                             "mismatches_vs_one_gpu": int((jg != one_g).sum() + (jl != one_l).sum())}
+            log("scaling check: %s" % scaling_check)
 
     per_step_ms = ms / args.steps
-    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes()), plain_ms],
+    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes()), plain_ms, ceiling],
                          dtype=torch.float64, device="cuda")
+    alg_bytes = float(w.algorithmic_bytes())
+    ceiling_sum = ceiling
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         per_step_ms, e2e_ms, kernel_ms, plain_ms = mx[0].item(), mx[1].item(), mx[2].item(), mx[5].item()
         total_bp = sm[3].item()
+        alg_bytes = sm[4].item() / world          # per GPU (mean) against the slowest GPU's kernel time
+        ceiling_sum = sm[6].item()
     else:
         total_bp = float(w.aligned_bp)
 
@@ -470,30 +557,44 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = w.algorithmic_bytes() / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        # DRAM bytes of one launch of the scoring kernel, measured under ncu by tools/measure_traffic.sh on the default N=1
+        # workload; quoted only while the kernel sources are the ones it was measured on (else null)
+        traffic, traffic_note = None, "not measured for this code / workload (tools/measure_traffic.sh)"
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if (tj.get("source_hash") == source_hash() and world == 1 and tj.get("blocks") == args.blocks
+                    and args.mean_log_len == 3.6 and not args.split and not args.fold):
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("how")
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": total_bp / (per_step_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+            "scaling": args.scaling if world > 1 else "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
             "e2e": {"value": total_bp / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": compact_bytes, "d2h_bytes_per_step": int(16 * len(w.jobs)),
+                    "h2d_bytes_per_step": compact_bytes, "d2h_bytes_per_step": int(16 * len(w.jobs) + 32 * len(part_local)),
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "parts_rank0": e2e_parts,
+                    # pinned host -> device rate of this box with all ranks copying at once, and how much of the e2e step the
+                    # bare copy of the step's bytes at that rate would take
+                    "h2d_ceiling_gbs_all_ranks": round(ceiling_sum, 1), "h2d_ceiling_gbs_rank0": round(ceiling, 1),
+                    "h2d_time_fraction_of_step": round((compact_bytes / (ceiling * 1e9)) / (e2e_ms * 1e-3), 3),
                     "call": "gat_score_compact: work-list as a .chain file stores it (6-byte size/gap blocks, 8-byte chains), expanded on the device",
                     "plain_records": {"call": "gat_score: 12-byte absolute blocks, 24-byte jobs", "value": total_bp / (plain_ms * 1e-3) / 1e9,
                                       "ms_per_step": plain_ms, "h2d_bytes_per_step": plain_bytes}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "kernel": "scoreChunksKernel",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": w.algorithmic_bytes()},
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                         "kernel": "scoreTilesKernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "algorithmic_bytes": "SURVEY 8d: 0.5 B per aligned bp + 12 B per block + 40 B per job"},
             "clocks": clocks,
             "aligned_bp_per_gpu": w.aligned_bp, "chains_per_gpu": int(len(w.jobs)), "genome_upload_s": round(upload_s, 3),
         }
+        if scaling_check is not None:
+            line["scaling_check"] = scaling_check
+            if scaling_check["mismatches_vs_one_gpu"]:
+                raise SystemExit("bench: %d scores of the sharded run differ from one GPU" % scaling_check["mismatches_vs_one_gpu"])
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.time()
             res = cpu_reference(w, 2, 1, int(args.cpu_sample_mbp * 1e6), gpu_scores=(g_res, l_res))

@@ -13,6 +13,7 @@ SYMBOLS = [
     "gat_set_scoring", "gat_score", "gat_worklist_create", "gat_worklist_run", "gat_worklist_results",
     "gat_worklist_destroy", "gat_synchronize", "gat_get_stats", "gat_set_profiling",
     "gat_host_alloc", "gat_host_free", "gat_max_record_bases", "gat_crossover", "gat_score_compact",
+    "gat_request_tuples", "gat_tuple_join", "gat_tuple_scores", "gat_gap_cost",
 ]
 
 
@@ -58,6 +59,12 @@ def load():
     lib.gat_worklist_destroy.restype = None
     lib.gat_crossover.argtypes = [vp, vp, u64, vp, vp]
     lib.gat_score_compact.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
+    lib.gat_gap_cost.argtypes = [vp, vp, vp, u64, vp]
+    lib.gat_request_tuples.argtypes = [vp, vp, u64, vp]
+    lib.gat_tuple_join.argtypes = [vp, ctypes.c_int64, vp]
+    lib.gat_tuple_join.restype = None
+    lib.gat_tuple_scores.argtypes = [vp, vp, vp]
+    lib.gat_tuple_scores.restype = None
     lib.gat_max_record_bases.argtypes = [vp]
     lib.gat_max_record_bases.restype = ctypes.c_uint32
     lib.gat_synchronize.argtypes = [vp]

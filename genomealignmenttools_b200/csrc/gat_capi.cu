@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "gat.h"
@@ -38,13 +39,14 @@ struct GenomeDev {
     long long *seqBase = nullptr;
     uint32_t *seqSize = nullptr;
     uint32_t nSeq = 0;
+    uint32_t words = 0;
     bool loaded = false;
     void release()
     {
         cudaFree(planes); cudaFree(nplane); cudaFree(nwin); cudaFree(nwin2); cudaFree(seqBase); cudaFree(seqSize);
         planes = nullptr; nplane = nwin = nullptr; nwin2 = nullptr; seqBase = nullptr; seqSize = nullptr; nSeq = 0; loaded = false;
     }
-    GenomeView view() const { return GenomeView{planes, nplane, nwin, nwin2, (const int64_t *)seqBase, seqSize, nSeq}; }
+    GenomeView view() const { return GenomeView{planes, nplane, nwin, nwin2, (const int64_t *)seqBase, seqSize, nSeq, words}; }
 };
 
 struct gat_ctx {
@@ -74,6 +76,8 @@ struct gat_ctx {
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
     uint32_t smallBases = 1;
     bool oldKernel = false;            // GAT_KERNEL=chunks in the environment: the round-1 scoring kernel (A/B measurements)
+    std::vector<uint32_t> partJobs;    // gat_request_tuples(): jobs of the next scoring call whose tuple the caller wants
+    gat_tuple *partOut = nullptr;
 };
 
 struct gat_worklist {
@@ -91,12 +95,15 @@ struct gat_worklist {
     Tup *chunkHead = nullptr, *chunkTail = nullptr;
     int *chunkTailJob = nullptr;
     long long *outGlobal = nullptr, *outLocal = nullptr;
+    Tup *outTuple = nullptr;            // per job, only when tuples were requested (written by the fix-up kernel)
+    uint64_t capTuples = 0;
 };
 
 static void freeWorklistBuffers(gat_worklist *wl)
 {
     cudaFree(wl->jobs); cudaFree(wl->info); if (!wl->borrowedBlocks) cudaFree(wl->blocks); cudaFree(wl->chunkJob); cudaFree(wl->headBits); cudaFree(wl->chunkHead);
-    cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal);
+    cudaFree(wl->chunkTail); cudaFree(wl->chunkTailJob); cudaFree(wl->outGlobal); cudaFree(wl->outLocal); cudaFree(wl->outTuple);
+    wl->outTuple = nullptr; wl->capTuples = 0;
     wl->jobs = nullptr; wl->info = nullptr; wl->blocks = nullptr; wl->chunkJob = nullptr; wl->headBits = nullptr; wl->chunkHead = wl->chunkTail = nullptr;
     wl->chunkTailJob = nullptr; wl->outGlobal = wl->outLocal = nullptr;
     wl->capJobs = wl->capBlocks = wl->capChunks = 0;
@@ -273,6 +280,7 @@ extern "C" int gat_load_genome(gat_ctx *ctx, int side, const uint8_t *packed, ui
 #undef CUG
     cleanup();
     g.nSeq = nSeq;
+    g.words = (uint32_t)(totalBases / 32);
     g.loaded = true;
     return GAT_OK;
 }
@@ -479,6 +487,24 @@ static ScoreParams scoreParams(gat_ctx *ctx, gat_worklist *wl)
     return P;
 }
 
+// gat_request_tuples(): the fix-up kernel also stores the tuple of every job it finishes; the buffer exists only then
+static int ensureTupleBuffer(gat_ctx *ctx, gat_worklist *wl)
+{
+    if (ctx->partJobs.empty()) return GAT_OK;
+    if (wl->capTuples < wl->nJobs) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(wl->outTuple);
+        wl->outTuple = nullptr; wl->capTuples = 0;
+        CU(cudaMalloc(&wl->outTuple, (wl->nJobs + 1) * sizeof(Tup)));
+        wl->capTuples = wl->nJobs;
+    }
+    for (uint32_t j : ctx->partJobs) {
+        if (j >= wl->nJobs) return fail(GAT_EINVAL, "gat_request_tuples: job %u out of range", j);
+        CU(cudaMemsetAsync(wl->outTuple + j, 0x80, sizeof(Tup), ctx->stream));     // recognisable if the fix-up kernel never writes it
+    }
+    return GAT_OK;
+}
+
 // bitmap reset + jobPrepKernel: needs the jobs only, not the block records
 static int launchPrep(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 {
@@ -521,7 +547,8 @@ static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t c
 static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 {
     fixupKernel<<<(wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
-                                                                           wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->err);
+                                                                           wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal,
+                                                                           ctx->partJobs.empty() ? nullptr : wl->outTuple, ctx->err);
 }
 
 extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
@@ -539,10 +566,12 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
         CU(cudaMemsetAsync(wl->outLocal, 0, wl->nJobs * sizeof(long long), st));
         return GAT_OK;
     }
+    int rc = ensureTupleBuffer(ctx, wl);
+    if (rc != GAT_OK) return rc;
     ScoreParams P = scoreParams(ctx, wl);
     const bool prof = ctx->profiling;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
-    int rc = launchPrep(ctx, wl, st);
+    rc = launchPrep(ctx, wl, st);
     if (rc != GAT_OK) return rc;
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
     const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, st);
@@ -631,10 +660,20 @@ extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *glo
         if (global) CU(cudaMemcpyAsync(global, wl->outGlobal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         if (local) CU(cudaMemcpyAsync(local, wl->outLocal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    std::vector<uint32_t> parts;
+    parts.swap(ctx->partJobs);          // a request covers one scoring call
+    if (!parts.empty()) {
+        if (!wl->outTuple || wl->capTuples < wl->nJobs) return fail(GAT_ESTATE, "gat_request_tuples must precede the scoring call");
+        for (size_t k = 0; k < parts.size(); k++)
+            CU(cudaMemcpyAsync(ctx->partOut + k, wl->outTuple + parts[k], sizeof(gat_tuple), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     int err = 0;
     int rc = readDeviceError(ctx, &err);
     if (rc != GAT_OK) return rc;
     if (err & ~ERR_EMPTYJOB) return rejectWorklist(err);
+    for (size_t k = 0; k < parts.size(); k++)       // still the fill pattern: the job was not finished by the fix-up kernel
+        if ((uint64_t)ctx->partOut[k].c == 0x8080808080808080ull)
+            return fail(GAT_EINVAL, "gat_request_tuples: job %u owns fewer than GAT_TUPLE_MIN_BLOCKS job-blocks", parts[k]);
     if (err & ERR_EMPTYJOB) {
         rc = rerunWithoutEmptyJobs(ctx, wl, global, local);
         if (rc != GAT_OK) return rc;
@@ -725,6 +764,8 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
         CU(cudaMemsetAsync(wl->outGlobal, 0, nJobs * sizeof(long long), st));
         CU(cudaMemsetAsync(wl->outLocal, 0, nJobs * sizeof(long long), st));
     } else {
+        rc = ensureTupleBuffer(ctx, wl);
+        if (rc != GAT_OK) return rc;
         const ScoreParams P = scoreParams(ctx, wl);
         if (slices == 1) {
             CU(cudaMemcpyAsync(base + oBlocks, blocks, nBlocks * sizeof(gat_cblock), cudaMemcpyHostToDevice, st));
@@ -807,6 +848,28 @@ extern "C" int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPai
     return rc;
 }
 
+extern "C" int gat_gap_cost(gat_ctx *ctx, const int32_t *dq, const int32_t *dt, uint64_t n, int32_t *out)
+{
+    if (!ctx || (n && (!dq || !dt || !out))) return fail(GAT_EINVAL, "gat_gap_cost: NULL argument");
+    if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_gap_cost: call gat_set_scoring first");
+    if (n == 0) return GAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    int *d = nullptr;
+    CU(cudaMalloc(&d, 3 * n * sizeof(int)));
+    cudaError_t e = cudaMemcpyAsync(d, dq, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, dt, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        gapBatchKernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->gap, ctx->gapSmall, ctx->gapDense, ctx->gapLongPos, ctx->gapLongVal,
+                                                                           d, d + n, n, d + 2 * n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * n, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(GAT_ECUDA, "gat_gap_cost failed: %s", cudaGetErrorString(e));
+    return GAT_OK;
+}
+
 extern "C" uint32_t gat_max_record_bases(const gat_ctx *ctx) { return ctx ? ctx->maxBlockBases : 0; }
 
 #ifdef GAT_TIMING
@@ -842,6 +905,37 @@ extern "C" int gat_set_profiling(gat_ctx *ctx, int on)
     if (!ctx) return fail(GAT_EINVAL, "gat_set_profiling: NULL ctx");
     ctx->profiling = on != 0;
     return GAT_OK;
+}
+
+extern "C" int gat_request_tuples(gat_ctx *ctx, const uint32_t *jobIx, uint64_t n, gat_tuple *out)
+{
+    if (!ctx || (n && (!jobIx || !out))) return fail(GAT_EINVAL, "gat_request_tuples: NULL argument");
+    ctx->partJobs.assign(jobIx, jobIx + n);
+    ctx->partOut = out;
+    return GAT_OK;
+}
+
+// acc = acc (+) [peak test, gap, clamp at 0] (+) next: what chainCalcScoreLocal does between the last block of one part
+// and the first block of the next (scoreChain.c:181-195), as tuples (see Tup in gat_kernels.cuh)
+extern "C" void gat_tuple_join(gat_tuple *acc, int64_t gapCost, const gat_tuple *next)
+{
+    const Tup a{acc->d, acc->c, acc->e, acc->f}, x{-gapCost, 0, 0, NEG}, b{next->d, next->c, next->e, next->f};
+    auto comb = [](const Tup &p, const Tup &q) {
+        Tup r;
+        r.d = p.d + q.d;
+        r.c = std::max(q.c, p.c + q.d);
+        r.e = std::max(p.e, p.d + q.e);
+        r.f = std::max(std::max(p.f, q.f), p.c + q.e);
+        return r;
+    };
+    const Tup r = comb(comb(a, x), b);
+    acc->d = r.d; acc->c = r.c; acc->e = r.e; acc->f = r.f;
+}
+
+extern "C" void gat_tuple_scores(const gat_tuple *t, int64_t *global, int64_t *local)
+{
+    if (global) *global = t->d;
+    if (local) *local = std::max<int64_t>(0, std::max(std::max(t->c, t->d), std::max(t->e, t->f)));
 }
 
 extern "C" void *gat_host_alloc(size_t bytes)

@@ -51,6 +51,7 @@ struct GenomeView {
     const int64_t *seqBase;   // first base of each sequence in the padded coordinate (multiple of 128)
     const uint32_t *seqSize;
     uint32_t nSeq;
+    uint32_t words;           // 32-base words in `planes`
 };
 
 // (d, c, e, f): effect of a run of blocks on the local-score state.  Entering with running
@@ -207,11 +208,22 @@ __device__ __forceinline__ int gapCostOf(const GapView &g, const int *small, con
     return gapCostExact(g, small, longPos, longVal, (int)which, (int)v);
 }
 
+// gapCalcCost for a batch of (dq, dt) pairs, by the routines the scoring kernel uses (dense table, then the exact one)
+__global__ void gapBatchKernel(GapView g, const int *__restrict__ small, const int *__restrict__ dense, const int *__restrict__ longPos,
+                               const double *__restrict__ longVal, const int *__restrict__ dq, const int *__restrict__ dt,
+                               unsigned long long n, int *__restrict__ out);
 __global__ void gapDenseKernel(GapView g, const int *__restrict__ small, const int *__restrict__ longPos,
                                const double *__restrict__ longVal, int *__restrict__ dense)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x, which = blockIdx.y;
     if (v < g.denseSize) dense[(size_t)which * g.denseSize + v] = gapCostExact(g, small, longPos, longVal, which, v);
+}
+__global__ void gapBatchKernel(GapView g, const int *__restrict__ small, const int *__restrict__ dense, const int *__restrict__ longPos,
+                               const double *__restrict__ longVal, const int *__restrict__ dq, const int *__restrict__ dt,
+                               unsigned long long n, int *__restrict__ out)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gapCost(g, small, dense, longPos, longVal, dq[i], dt[i]);
 }
 
 // ------------------------------------------------------------------ base windows
@@ -886,7 +898,7 @@ __global__ void __launch_bounds__(FIX_TPB)
 fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned long long total,
             const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
             const int *__restrict__ chunkTailJob, uint32_t nChunks,
-            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, const int *__restrict__ err)
+            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, Tup *__restrict__ outTuple, const int *__restrict__ err)
 {
     __shared__ uint32_t sLongC[FIX_TPB], sLongN[FIX_TPB];
     __shared__ int sLongJ[FIX_TPB];
@@ -908,6 +920,7 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
             const Tup all = tupCombine(loadTup(chunkTail + c), foldSlice(chunkHead, c + 1, count));
             outGlobal[j] = all.d;
             outLocal[j] = finalLocal(all);
+            if (outTuple) outTuple[j] = all;        // the job as a map on the local-score state (parts of a chain split over GPUs)
         } else {
             const int k = atomicAdd(&sNLong, 1);
             sLongC[k] = c; sLongN[k] = count; sLongJ[k] = j;
@@ -928,6 +941,7 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
             for (int w = 0; w < FIX_TPB / 32; w++) all = tupCombine(all, sPart[w]);
             outGlobal[sLongJ[e]] = all.d;
             outLocal[sLongJ[e]] = finalLocal(all);
+            if (outTuple) outTuple[sLongJ[e]] = all;
         }
         __syncthreads();
     }

@@ -969,17 +969,63 @@ MultiGpu::MultiGpu(int nGpus)
 {
     const int have = gat_device_count();
     if (have == 0) fail("no CUDA device: chain scoring has no CPU path (%s)", gat_last_error());
-    if (nGpus > have) fail("-gpus=%d but only %d CUDA device(s) visible", nGpus, have);
-    for (int d = 0; d < nGpus; d++) {
+    std::vector<int> devices;
+    if (const char *list = getenv("GAT_DEVICES")) {         // e.g. "0,0": two contexts on one device
+        for (const char *p = list; *p;) {
+            devices.push_back(atoi(p));
+            while (*p && *p != ',') p++;
+            if (*p == ',') p++;
+        }
+        if ((int)devices.size() < nGpus) fail("-gpus=%d but GAT_DEVICES names %d device(s)", nGpus, (int)devices.size());
+        devices.resize(nGpus);
+    } else {
+        if (nGpus > have) fail("-gpus=%d but only %d CUDA device(s) visible", nGpus, have);
+        for (int d = 0; d < nGpus; d++) devices.push_back(d);
+    }
+    for (int d : devices) {
         gat_ctx *c = nullptr;
         if (gat_create(&c, d, nullptr) != GAT_OK) fail("%s", gat_last_error());
         ctx.push_back(c);
     }
+    staging_.resize(ctx.size());
 }
 
 MultiGpu::~MultiGpu()
 {
+    for (auto &st : staging_) gat_host_free(st.p);
     for (gat_ctx *c : ctx) gat_destroy(c);
+}
+
+void *MultiGpu::pinned(size_t g, size_t bytes)
+{
+    Staging &st = staging_[g];
+    if (bytes > st.cap) {
+        gat_host_free(st.p);
+        st.cap = bytes + bytes / 4 + 4096;
+        st.p = gat_host_alloc(st.cap);
+        if (!st.p) { st.cap = 0; fail("%s", gat_last_error()); }
+    }
+    return st.p;
+}
+
+void MultiGpu::prepare(const TwoBitFile &tbT, const std::vector<int> &useT, const TwoBitFile &tbQ, const std::vector<int> &useQ,
+                       const ScoreScheme &ss, const GapCalc &gc)
+{
+    gap_ = gc;
+    haveGap_ = true;
+    std::vector<std::string> errors(ctx.size());
+    std::vector<std::thread> threads;
+    for (size_t g = 0; g < ctx.size(); g++)
+        threads.emplace_back([&, g]() {
+            try {
+                uploadGenome(ctx[g], GAT_TARGET, tbT, useT);
+                uploadGenome(ctx[g], GAT_QUERY, tbQ, useQ);
+                setScoring(ctx[g], ss, gc);
+            } catch (const Error &e) { errors[g] = e.message; }
+        });
+    for (auto &t : threads) t.join();
+    for (const auto &e : errors)
+        if (!e.empty()) fail("%s", e.c_str());
 }
 
 // ------------------------------------------------------------------ chainRemovePartialOverlaps
@@ -1186,42 +1232,168 @@ bool packCompact(const WorkList &wl, CompactWorkList &out)
 
 void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local)
 {
-    global.assign(wl.jobs.size(), 0);
-    local.assign(wl.jobs.size(), 0);
+    const size_t nJobs = wl.jobs.size(), nGpus = ctx.size();
+    global.assign(nJobs, 0);
+    local.assign(nJobs, 0);
+    lastShards.assign(nGpus, ShardStats());
     if (wl.jobs.empty()) return;
-    if (ctx.size() == 1) {
+    if (nGpus == 1) {
         CompactWorkList cw;
+        lastShards[0].jobs = nJobs; lastShards[0].records = wl.blocks.size();
         if (packCompact(wl, cw)) {      // whole chains (scoreChain): half the bytes over PCIe
+            lastShards[0].compact = true;
+            lastShards[0].h2dBytes = cw.jobs.size() * sizeof(gat_cjob) + cw.blocks.size() * sizeof(gat_cblock) + (cw.abs.size() + cw.anchors.size()) * sizeof(gat_cabs);
             if (gat_score_compact(ctx[0], cw.jobs.data(), cw.jobs.size(), cw.blocks.data(), cw.blocks.size(), cw.abs.data(), cw.abs.size(),
                                   cw.anchors.data(), global.data(), local.data()) != GAT_OK)
                 fail("%s", gat_last_error());
+            if (getenv("GAT_TOOL_TIMING"))
+                fprintf(stderr, "gpu shard 0: %llu jobs, %llu records, %llu bytes host->device (compact), 0 pieces of cut chains\n",
+                        (unsigned long long)nJobs, (unsigned long long)wl.blocks.size(), (unsigned long long)lastShards[0].h2dBytes);
             return;
         }
-        if (gat_score(ctx[0], wl.jobs.data(), wl.jobs.size(), wl.totalJobBlocks, wl.blocks.data(), wl.blocks.size(),
+        lastShards[0].h2dBytes = nJobs * sizeof(gat_job) + wl.blocks.size() * sizeof(gat_block);
+        if (gat_score(ctx[0], wl.jobs.data(), nJobs, wl.totalJobBlocks, wl.blocks.data(), wl.blocks.size(),
                       global.data(), local.data()) != GAT_OK)
             fail("%s", gat_last_error());
+        if (getenv("GAT_TOOL_TIMING"))
+            fprintf(stderr, "gpu shard 0: %llu jobs, %llu records, %llu bytes host->device (plain), 0 pieces of cut chains\n",
+                    (unsigned long long)nJobs, (unsigned long long)wl.blocks.size(), (unsigned long long)lastShards[0].h2dBytes);
         return;
     }
-    // one host thread per GPU; every GPU holds a full genome copy, shards are independent (no collective)
-    const auto shards = shardJobs(wl, (int)ctx.size());
-    std::vector<std::string> errors(ctx.size());
-    std::vector<std::thread> threads;
-    for (size_t g = 0; g < ctx.size(); g++)
-        threads.emplace_back([&, g]() {
-            std::vector<gat_job> jobs;
-            uint64_t total = 0;
-            extractShard(wl, shards[g], jobs, total);
-            std::vector<int64_t> gl(jobs.size()), lo(jobs.size());
-            if (!jobs.empty() &&
-                gat_score(ctx[g], jobs.data(), jobs.size(), total, wl.blocks.data(), wl.blocks.size(), gl.data(), lo.data()) != GAT_OK) {
-                errors[g] = gat_last_error();
-                return;
+
+    // ---- pieces: every job is one piece, except whole-chain jobs above 1/(4 nGpus) of the aligned bases
+    struct Piece { uint32_t job; uint64_t first, count; int64_t weight; };
+    std::vector<Piece> pieces;
+    std::vector<uint32_t> firstPiece(nJobs + 1);
+    int64_t allBases = 0;
+    for (size_t j = 0; j < nJobs; j++) allBases += std::max<int64_t>(wl.aliBases[j], 0);
+    const int64_t limit = std::max<int64_t>(1, allBases / (4 * (int64_t)nGpus));
+    pieces.reserve(nJobs + 8 * nGpus);
+    for (size_t j = 0; j < nJobs; j++) {
+        const gat_job &job = wl.jobs[j];
+        const uint64_t count = (j + 1 < nJobs ? wl.jobs[j + 1].blockPtr : wl.totalJobBlocks) - job.blockPtr;
+        firstPiece[j] = (uint32_t)pieces.size();
+        const bool whole = job.clipStart == GAT_NO_CLIP_START && job.clipEnd == GAT_NO_CLIP_END;
+        if (haveGap_ && whole && wl.aliBases[j] > limit && count >= 2 * (uint64_t)GAT_TUPLE_MIN_BLOCKS) {
+            const int k = (int)((wl.aliBases[j] + limit - 1) / limit);
+            std::vector<uint64_t> cuts{0};          // records (within the job) at which a piece starts
+            uint64_t i = 0;
+            int64_t run = 0;
+            for (int part = 1; part < k; part++) {
+                const int64_t until = wl.aliBases[j] * part / k;
+                while (i < count && run < until) { run += wl.blocks[job.firstBlock + i].size & 0x7fffffffu; i++; }
+                // never start a piece with a continuation record; a piece (and what is left behind it) must be long enough for
+                // the fix-up kernel to finish it
+                while (i < count && (wl.blocks[job.firstBlock + i].size & GAT_BLOCK_JOINED)) { run += wl.blocks[job.firstBlock + i].size & 0x7fffffffu; i++; }
+                if (i - cuts.back() >= GAT_TUPLE_MIN_BLOCKS && count - i >= GAT_TUPLE_MIN_BLOCKS) cuts.push_back(i);
             }
-            for (size_t k = 0; k < jobs.size(); k++) { global[shards[g][k]] = gl[k]; local[shards[g][k]] = lo[k]; }
+            for (size_t c = 0; c < cuts.size(); c++)
+                pieces.push_back(Piece{(uint32_t)j, job.firstBlock + cuts[c], (c + 1 < cuts.size() ? cuts[c + 1] : count) - cuts[c], 0});
+        } else pieces.push_back(Piece{(uint32_t)j, job.firstBlock, count, 0});
+    }
+    firstPiece[nJobs] = (uint32_t)pieces.size();
+    for (Piece &p : pieces) {
+        int64_t bases = 0;
+        if (firstPiece[p.job + 1] - firstPiece[p.job] == 1) bases = std::max<int64_t>(wl.aliBases[p.job], 0);
+        else for (uint64_t r = 0; r < p.count; r++) bases += wl.blocks[p.first + r].size & 0x7fffffffu;
+        p.weight = bases + 64 * (int64_t)p.count + 64;      // short blocks cost more per base than long ones
+    }
+    // ---- greedy longest-processing-time balance of the pieces
+    std::vector<uint32_t> order(pieces.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pieces[a].weight > pieces[b].weight; });
+    typedef std::pair<int64_t, int> Load;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (size_t g = 0; g < nGpus; g++) heap.push(Load(0, (int)g));
+    std::vector<std::vector<uint32_t>> shard(nGpus);
+    for (uint32_t pi : order) {
+        Load l = heap.top();
+        heap.pop();
+        shard[l.second].push_back(pi);
+        heap.push(Load(l.first + pieces[pi].weight, l.second));
+    }
+    for (auto &v : shard) std::sort(v.begin(), v.end());        // file order inside a shard: neighbours share sectors
+
+    // ---- one host thread per GPU: compact the shard's records, stage them in pinned memory, score
+    std::vector<int64_t> pGlobal(pieces.size()), pLocal(pieces.size());
+    std::vector<gat_tuple> pTuple(pieces.size());
+    std::vector<std::string> errors(nGpus);
+    std::vector<std::thread> threads;
+    for (size_t g = 0; g < nGpus; g++)
+        threads.emplace_back([&, g]() {
+            try {
+                const std::vector<uint32_t> &mine = shard[g];
+                if (mine.empty()) return;
+                WorkList sw;            // the shard as a work-list of its own: records copied range by range
+                sw.jobs.resize(mine.size());
+                uint64_t total = 0;
+                for (uint32_t pi : mine) total += pieces[pi].count;
+                sw.blocks.resize(total);
+                std::vector<uint32_t> wantTuple;
+                uint64_t at = 0;
+                for (size_t k = 0; k < mine.size(); k++) {
+                    const Piece &p = pieces[mine[k]];
+                    gat_job job = wl.jobs[p.job];
+                    job.firstBlock = job.blockPtr = (uint32_t)at;
+                    sw.jobs[k] = job;
+                    memcpy(sw.blocks.data() + at, wl.blocks.data() + p.first, p.count * sizeof(gat_block));
+                    at += p.count;
+                    if (firstPiece[p.job + 1] - firstPiece[p.job] > 1) wantTuple.push_back((uint32_t)k);
+                }
+                sw.totalJobBlocks = total;
+                ShardStats &st = lastShards[g];
+                st.jobs = mine.size(); st.records = total; st.pieces = wantTuple.size();
+                std::vector<int64_t> gl(mine.size()), lo(mine.size());
+                std::vector<gat_tuple> tup(wantTuple.size());
+                if (!wantTuple.empty() && gat_request_tuples(ctx[g], wantTuple.data(), wantTuple.size(), tup.data()) != GAT_OK)
+                    fail("%s", gat_last_error());
+                CompactWorkList cw;
+                int rc;
+                if (packCompact(sw, cw)) {
+                    const size_t bj = cw.jobs.size() * sizeof(gat_cjob), bb = cw.blocks.size() * sizeof(gat_cblock),
+                                 ba = cw.abs.size() * sizeof(gat_cabs), bn = cw.anchors.size() * sizeof(gat_cabs);
+                    auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
+                    char *base = static_cast<char *>(pinned(g, up(bj) + up(bb) + up(ba) + up(bn) + 64));
+                    char *pj = base, *pb = pj + up(bj), *pa = pb + up(bb), *pn = pa + up(ba);
+                    memcpy(pj, cw.jobs.data(), bj); memcpy(pb, cw.blocks.data(), bb); memcpy(pa, cw.abs.data(), ba); memcpy(pn, cw.anchors.data(), bn);
+                    st.compact = true; st.h2dBytes = bj + bb + ba + bn;
+                    rc = gat_score_compact(ctx[g], reinterpret_cast<gat_cjob *>(pj), cw.jobs.size(), reinterpret_cast<gat_cblock *>(pb), cw.blocks.size(),
+                                           reinterpret_cast<gat_cabs *>(pa), cw.abs.size(), reinterpret_cast<gat_cabs *>(pn), gl.data(), lo.data());
+                } else {
+                    const size_t bj = sw.jobs.size() * sizeof(gat_job), bb = sw.blocks.size() * sizeof(gat_block);
+                    char *base = static_cast<char *>(pinned(g, bj + bb + 128));
+                    char *pj = base, *pb = base + ((bj + 63) & ~(size_t)63);
+                    memcpy(pj, sw.jobs.data(), bj); memcpy(pb, sw.blocks.data(), bb);
+                    st.h2dBytes = bj + bb;
+                    rc = gat_score(ctx[g], reinterpret_cast<gat_job *>(pj), sw.jobs.size(), total, reinterpret_cast<gat_block *>(pb), sw.blocks.size(),
+                                   gl.data(), lo.data());
+                }
+                if (rc != GAT_OK) fail("%s", gat_last_error());
+                for (size_t k = 0; k < mine.size(); k++) { pGlobal[mine[k]] = gl[k]; pLocal[mine[k]] = lo[k]; }
+                for (size_t k = 0; k < wantTuple.size(); k++) pTuple[mine[wantTuple[k]]] = tup[k];
+            } catch (const Error &e) { errors[g] = e.message; }
         });
     for (auto &t : threads) t.join();
     for (const auto &e : errors)
         if (!e.empty()) fail("%s", e.c_str());
+
+    if (getenv("GAT_TOOL_TIMING"))
+        for (size_t g = 0; g < nGpus; g++)
+            fprintf(stderr, "gpu shard %zu: %llu jobs, %llu records, %llu bytes host->device (%s), %llu pieces of cut chains\n", g,
+                    (unsigned long long)lastShards[g].jobs, (unsigned long long)lastShards[g].records, (unsigned long long)lastShards[g].h2dBytes,
+                    lastShards[g].compact ? "compact" : "plain", (unsigned long long)lastShards[g].pieces);
+    // ---- back to jobs; the pieces of a cut chain are joined in order with the gap cost between them
+    for (size_t j = 0; j < nJobs; j++) {
+        const uint32_t p0 = firstPiece[j], p1 = firstPiece[j + 1];
+        if (p1 - p0 == 1) { global[j] = pGlobal[p0]; local[j] = pLocal[p0]; continue; }
+        gat_tuple acc = pTuple[p0];
+        for (uint32_t p = p0 + 1; p < p1; p++) {
+            const gat_block &last = wl.blocks[pieces[p - 1].first + pieces[p - 1].count - 1], &first = wl.blocks[pieces[p].first];
+            const int ls = (int)(last.size & 0x7fffffffu);
+            gat_tuple_join(&acc, gap_.cost(first.qStart - (last.qStart + ls), first.tStart - (last.tStart + ls)), &pTuple[p]);
+        }
+        gat_tuple_scores(&acc, &global[j], &local[j]);
+    }
 }
 
 }  // namespace gathost

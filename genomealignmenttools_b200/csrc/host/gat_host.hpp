@@ -150,13 +150,30 @@ std::vector<std::vector<uint32_t>> shardJobs(const WorkList &wl, int parts);
 // Sub-work-list holding the given jobs (block records are shared, so only jobs are re-indexed).
 void extractShard(const WorkList &wl, const std::vector<uint32_t> &jobIx, std::vector<gat_job> &jobs, uint64_t &totalJobBlocks);
 
-// Score a work-list on `nGpus` devices (each with its own context, genomes already loaded by
-// `prepare(ctx)`); results land in global/local indexed like wl.jobs.
+// Score a work-list on `nGpus` devices, one context and one host thread per device; every device holds a full copy of
+// both genomes, shards are independent (no collective), results land in global/local indexed like wl.jobs.
+//   * a whole-chain job above 1/(4 nGpus) of the aligned bases is cut at block boundaries into pieces; a piece comes back
+//     as a tuple (gat_request_tuples) and the pieces are joined on the host with the gap cost between them, bit-identical
+//     to the unsplit chain;
+//   * jobs (and pieces) are balanced by greedy aligned-base load; every GPU receives only the records its jobs reference,
+//     from a pinned staging buffer, as a compact work-list (gat_score_compact) when the shard holds whole chains only.
+// Devices are 0..nGpus-1 unless GAT_DEVICES names them ("0,0" puts two contexts on device 0: how a one-GPU box tests this).
 struct MultiGpu {
     std::vector<gat_ctx *> ctx;
     explicit MultiGpu(int nGpus);
     ~MultiGpu();
+    // genomes and scoring parameters to every context (in parallel); the gap tables are kept for joining pieces
+    void prepare(const TwoBitFile &tbT, const std::vector<int> &useT, const TwoBitFile &tbQ, const std::vector<int> &useQ,
+                 const ScoreScheme &ss, const GapCalc &gc);
     void score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local);
+    struct ShardStats { uint64_t jobs = 0, records = 0, h2dBytes = 0, pieces = 0; bool compact = false; };
+    std::vector<ShardStats> lastShards;     // what the last score() sent to each GPU (tests, -verbose)
+private:
+    GapCalc gap_;
+    bool haveGap_ = false;
+    struct Staging { void *p = nullptr; size_t cap = 0; };
+    std::vector<Staging> staging_;          // pinned, one per GPU, grown on demand
+    void *pinned(size_t g, size_t bytes);
 };
 
 // chainRemovePartialOverlaps (kent/src/lib/chainConnect.c:255-344) for every chain of a set: where adjacent blocks

@@ -360,11 +360,7 @@ public:
             c.tSeq = (uint32_t)mapT[ti];
             c.qSeq = (uint32_t)mapQ[qi];
         }
-        for (gat_ctx *ctx : gpus.ctx) {
-            uploadGenome(ctx, GAT_TARGET, tbT, useT);
-            uploadGenome(ctx, GAT_QUERY, tbQ, useQ);
-            setScoring(ctx, ss, gc);
-        }
+        gpus.prepare(tbT, useT, tbQ, useQ, ss, gc);
     }
     // One batch: every request is one chainSubsetOnT + getChainScore of the reference.
     std::vector<SubScore> score(const std::vector<Request> &reqs)

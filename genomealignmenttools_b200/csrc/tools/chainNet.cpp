@@ -483,11 +483,7 @@ static int toolMain(int argc, char **argv)
         verbose(2, "rescoring %d partial fills (%llu job-blocks) on the GPU\n", (int)wl.jobs.size(), (unsigned long long)wl.totalJobBlocks);
         if (!wl.jobs.empty()) {
             MultiGpu &gpus = gpuStarter->get();
-            for (gat_ctx *ctx : gpus.ctx) {
-                uploadGenome(ctx, GAT_TARGET, tbT, useT);
-                uploadGenome(ctx, GAT_QUERY, tbQ, useQ);
-                setScoring(ctx, scheme, gapCalc);
-            }
+            gpus.prepare(tbT, useT, tbQ, useQ, scheme, gapCalc);
             phaseDone("contexts + genomes");
             gpus.score(wl, global, local);
             phaseDone("fills rescored on the GPU");

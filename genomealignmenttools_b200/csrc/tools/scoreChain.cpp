@@ -103,11 +103,7 @@ static int toolMain(int argc, char **argv)
     if (!cs.chains.empty()) {
         MultiGpu &gpus = gpuStarter.get();
         phaseDone("CUDA contexts");
-        for (gat_ctx *ctx : gpus.ctx) {
-            uploadGenome(ctx, GAT_TARGET, tbT, useT);
-            uploadGenome(ctx, GAT_QUERY, tbQ, useQ);
-            setScoring(ctx, scheme, gapCalc);
-        }
+        gpus.prepare(tbT, useT, tbQ, useQ, scheme, gapCalc);
         phaseDone("genomes uploaded");
         buildRecords(cs, wl);
         for (size_t c = 0; c < cs.chains.size(); c++) addChainJob(cs, c, chainT[c], chainQ[c], wl);

@@ -105,6 +105,23 @@ class ChainScorer:
         self._check(self.lib.gat_crossover(self.ctx, _ptr(pairs), len(pairs), _ptr(pos), _ptr(adj)))
         return pos, adj
 
+    def request_tuples(self, job_indices):
+        """gat_request_tuples: ask the next scoring call for the (d, c, e, f) tuples of the listed jobs (parts of chains that
+        were split over GPUs).  Returns the array the call will fill (sharding.TUPLE_DTYPE)."""
+        from .sharding import TUPLE_DTYPE
+        idx = np.ascontiguousarray(job_indices, dtype=np.uint32)
+        out = np.zeros(len(idx), dtype=TUPLE_DTYPE)
+        self._keep = [idx, out]          # must outlive the scoring call
+        self._check(self.lib.gat_request_tuples(self.ctx, _ptr(idx), len(idx), _ptr(out)))
+        return out
+
+    def gap_cost(self, dq, dt):
+        """gat_gap_cost: gapCalcCost for arrays of (dq, dt) on the device."""
+        dq = np.ascontiguousarray(dq, dtype=np.int32); dt = np.ascontiguousarray(dt, dtype=np.int32)
+        out = np.zeros(len(dq), dtype=np.int32)
+        self._check(self.lib.gat_gap_cost(self.ctx, _ptr(dq), _ptr(dt), len(dq), _ptr(out)))
+        return out
+
     def max_record_bases(self):
         """Longest record (gat_block.size) the device accepts under the current scoring parameters."""
         return int(self.lib.gat_max_record_bases(self.ctx))

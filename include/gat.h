@@ -184,6 +184,27 @@ typedef struct gat_xpair {
 } gat_xpair;
 int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPairs, int32_t *pos, int32_t *adjust);
 
+/* Chains split over several GPUs (a job with more than ~1/(4 nGPU) of the aligned bases is cut at block
+ * boundaries).  A part is scored as a job of its own; its global score alone cannot be joined into the chain's local
+ * score (chainCalcScoreLocal clamps at 0 and keeps a running maximum, src/scoreChain/scoreChain.c:181-195), so a part
+ * comes back as the 4-number tuple (d, c, e, f) meaning "entered with running score s and best M, the part leaves
+ * s' = max(c, s + d) and M' = max(M, s + e, f)"; d alone is the part's global score.  Parts join on the host:
+ *     acc = tuple(part 0); for every further part: gat_tuple_join(&acc, gapCalcCost between the parts, &tuple(part));
+ *     gat_tuple_scores(&acc, &global, &local);
+ * which is bit-identical to scoring the unsplit chain.  gat_request_tuples() names the jobs of the NEXT scoring call on the
+ * context (gat_score, gat_score_compact or gat_worklist_run + gat_worklist_results) whose tuples are wanted; out[k] is
+ * filled when that call returns its results.  Every such job must own at least GAT_TUPLE_MIN_BLOCKS job-blocks (parts
+ * are large by construction) and must not start with a GAT_BLOCK_JOINED record. */
+#define GAT_TUPLE_MIN_BLOCKS 1024u
+typedef struct gat_tuple { int64_t d, c, e, f; } gat_tuple;
+int gat_request_tuples(gat_ctx *ctx, const uint32_t *jobIx, uint64_t n, gat_tuple *out);
+void gat_tuple_join(gat_tuple *acc, int64_t gapCost, const gat_tuple *next);
+void gat_tuple_scores(const gat_tuple *t, int64_t *global, int64_t *local);
+
+/* gapCalcCost (kent/src/lib/gapCalc.c:298-331) for a batch of (dq, dt) pairs, evaluated on the device by the routines the
+ * scoring kernel uses, under the tables of gat_set_scoring.  (kent's own gapCalcCost in include/gat_kent.h is this with n = 1.) */
+int gat_gap_cost(gat_ctx *ctx, const int32_t *dq, const int32_t *dt, uint64_t n, int32_t *out);
+
 int gat_synchronize(gat_ctx *ctx);
 int gat_get_stats(gat_ctx *ctx, gat_stats *out);
 /* When on, gat_worklist_run/gat_score bracket each kernel with CUDA events (filled into gat_stats). */

@@ -402,3 +402,49 @@ def test_resident_worklist_matches_one_shot():
         wl.free()
     assert np.array_equal(g, g2) and np.array_equal(l, l2)
     assert st["kernel_launches"] == 3 and st["score_kernel_ms"] > 0
+
+
+@pytest.mark.parametrize("pieces_share", [400_000, 1_500_000])
+def test_chain_split_into_pieces_joins_to_the_unsplit_scores(oracle, tmp_path, pieces_share):
+    """a giant chain cut at block boundaries, its pieces scored as jobs of their own (as if on different GPUs),
+    joined on the host from their tuples (gat_request_tuples, gat_tuple_join): bit-identical to the unsplit chain and to
+    the oracle, through gat_score, the resident work-list and gat_score_compact."""
+    from genomealignmenttools_b200 import sharding
+    from genomealignmenttools_b200.records import pack_compact
+    w = synth.make_workload(["chrA", "chrB"], [40_000_000, 9_000_000], ["chrX", "chrY"], [36_000_000, 8_000_000], 90_000,
+                            seed=21, telomere_n=2000, n_fraction=0.002, zipf_s=1.2, max_chain_blocks=30_000)
+    scoring = Scoring(None, "medium")
+    paths = helpers.write_case(w, ["chrA", "chrB"], ["chrX", "chrY"], str(tmp_path))
+    og, ol, _ = oracle.score_jobs(oracle.scoring(None, "medium"), oracle.genome(paths["t"]), oracle.genome(paths["q"]),
+                                  w.jobs, w.total, w.blocks)
+    pj, origin, first_piece = sharding.split_giant_jobs(w.jobs, w.total, w.blocks, 2, share=pieces_share)
+    cut = np.nonzero(np.diff(first_piece) > 1)[0]
+    assert len(cut) >= 1
+    part_ix = np.concatenate([np.arange(first_piece[j], first_piece[j + 1]) for j in cut])
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(scoring)
+        wg, wl_ = sc.score(w.jobs, w.total, w.blocks)
+        assert np.array_equal(wg, og) and np.array_equal(wl_, ol)
+        results = []
+        tup = sc.request_tuples(part_ix)
+        g, l = sc.score(pj, w.total, w.blocks)
+        results.append((g, l, tup.copy()))
+        res = sc.upload(pj, w.total, w.blocks)
+        tup = sc.request_tuples(part_ix)
+        res.run()
+        g, l = res.results()
+        results.append((g, l, tup.copy()))
+        res.free()
+        cj, cb, ab, an = pack_compact(pj, w.total, w.blocks)
+        tup = sc.request_tuples(part_ix)
+        g, l = sc.score_compact(cj, cb, ab, an)
+        results.append((g, l, tup.copy()))
+        # a request names jobs that the fix-up kernel finishes: a short job is refused
+        short = np.nonzero(job_block_counts(pj, w.total) < 200)[0][:1]
+        sc.request_tuples(short)
+        with pytest.raises(GatError):
+            sc.score(pj, w.total, w.blocks)
+    for g, l, tup in results:
+        tuples = {int(p): tup[k] for k, p in enumerate(part_ix)}
+        jg, jl = sharding.join_pieces(w.jobs, w.total, w.blocks, pj, origin, first_piece, g, l, tuples, scoring.gap.cost)
+        assert np.array_equal(jg, og) and np.array_equal(jl, ol)

@@ -37,6 +37,20 @@ def test_libgathost_exports_every_declared_symbol():
         assert hasattr(lib, n), n
 
 
+def test_libgatkent_exports_kents_entry_points():
+    """include/gat_kent.h: kent's names (chainConnect.h:34-44, gapCalc.h:11-35, axt.h:93-121) are exported by libgatkent.so."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "genomealignmenttools_b200", "libgatkent.so"))
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "gat_kent.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)) - {"defined"})
+    for n in ("chainScoreBlock", "chainCalcScore", "chainCalcScoreSubChain", "gapCalcCost", "gapCalcFromFile",
+              "axtScoreSchemeRead", "axtScoreSchemeDefault"):
+        assert n in names
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.gatKentLayout.restype = ctypes.c_long
+    assert lib.gatKentLayout(3) == 8 + 256 * 256 * 4 + 4 + 4 + 8      # struct axtScoreScheme, kent/src/inc/axt.h:83-91
+
+
 def test_record_layouts_match_header():
     assert BLOCK_DTYPE.itemsize == 12 and JOB_DTYPE.itemsize == 24 and NRUN_DTYPE.itemsize == 12
     assert ctypes.sizeof(_native.GatStats) == 40
@@ -358,3 +372,80 @@ def test_cli_usage_and_errors():
     assert r.returncode == 255 and "cannot specify both" in r.stderr
     r = subprocess.run([exe, "a", "b.2bit", "c.2bit", "d", "-linearGap=loose"], capture_output=True, text=True)
     assert r.returncode == 255 and r.stderr.startswith("ERROR: target 2bit file or nib directory b.2bit does not exist")
+
+
+# ----------------------------------------------------------------------------- chains split over GPUs
+def _local_global(a, g):
+    """chainCalcScore / chainCalcScoreLocal on block scores a[i] and gap costs g[i] (gap in front of block i; g[0] unused):
+    the loops of kent chainConnect.c:24-40 and src/scoreChain/scoreChain.c:181-195."""
+    score = 0
+    best = 0
+    glob = 0
+    for i in range(len(a)):
+        if i:
+            score -= g[i]
+            glob -= g[i]
+            if score < 0:
+                score = 0
+        score += a[i]
+        glob += a[i]
+        best = max(best, score)
+    return glob, best
+
+
+def _tuple_of(a, g):
+    """(d, c, e, f) of a run of blocks scored as a job of its own (first block: no gap, no peak test)."""
+    NEG = -(1 << 60)
+    d, c, e, f = a[0], NEG, NEG, NEG
+    for i in range(1, len(a)):
+        dy = a[i] - g[i]
+        d, c, e, f = d + dy, max(a[i], c + dy), max(e, d), max(f, c)
+    return d, c, e, f
+
+
+def test_tuple_join_reproduces_the_unsplit_chain():
+    """gat_tuple_join / gat_tuple_scores (include/gat.h): pieces of a chain scored apart and joined with the gap cost at
+    every cut give the scores of the whole chain, whatever the cuts."""
+    import ctypes
+    from genomealignmenttools_b200 import _native
+    from genomealignmenttools_b200.sharding import TUPLE_DTYPE
+    lib = _native.load()
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        n = int(rng.integers(2, 60))
+        a = [int(x) for x in rng.integers(-3000, 6000, n)]
+        g = [0] + [int(x) for x in rng.integers(0, 5000, n - 1)]
+        want = _local_global(a, g)
+        k = int(rng.integers(1, min(6, n)))
+        cuts = sorted(set(int(x) for x in rng.integers(1, n, k)))
+        bounds = [0] + cuts + [n]
+        acc = None
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            t = np.array([_tuple_of(a[lo:hi], [0] + g[lo + 1:hi])], dtype=TUPLE_DTYPE)
+            if acc is None:
+                acc = t.copy()
+            else:
+                lib.gat_tuple_join(acc.ctypes.data, g[lo], t.ctypes.data)
+        gg, ll = ctypes.c_int64(), ctypes.c_int64()
+        lib.gat_tuple_scores(acc.ctypes.data, ctypes.byref(gg), ctypes.byref(ll))
+        assert (gg.value, ll.value) == want, (trial, a, g, cuts)
+
+
+def test_split_giant_jobs_partitions_the_records():
+    from genomealignmenttools_b200 import sharding, synth
+    from genomealignmenttools_b200.records import job_block_counts, ali_bases, BLOCK_JOINED
+    jobs, total, blocks = synth.make_chains([60_000_000, 20_000_000], [50_000_000, 18_000_000], 150_000, seed=9,
+                                            zipf_s=1.3, max_chain_blocks=60_000)
+    pj, origin, first_piece = sharding.split_giant_jobs(jobs, total, blocks, 4)
+    counts = job_block_counts(pj, total)
+    assert counts.sum() == total and len(pj) > len(jobs)
+    # pieces tile the records of their job in order
+    oc = job_block_counts(jobs, total)
+    for j in np.nonzero(np.diff(first_piece) > 1)[0]:
+        p = np.arange(first_piece[j], first_piece[j + 1])
+        assert counts[p].sum() == oc[j] and counts[p].min() >= sharding.TUPLE_MIN_BLOCKS
+        fb = pj["firstBlock"][p].astype(np.int64)
+        assert fb[0] == jobs["firstBlock"][j] and np.array_equal(fb[1:], fb[:-1] + counts[p][:-1])
+        assert not (blocks["size"][fb] & np.uint32(BLOCK_JOINED)).any()
+    limit = ali_bases(jobs, total, blocks).sum() // 16
+    assert ali_bases(pj, total, blocks).max() <= 2 * limit + 1
