@@ -34,12 +34,12 @@ def genomewide(golden):
     sc = ChainScorer(0)
     sc.load_genome("t", t); sc.load_genome("q", q)
     sc.set_scoring(Scoring(None, "medium"))
-    yield sc, jobs, total, blocks
+    yield sc, jobs, total, blocks, (t, q, tn, qn)
     sc.close()
 
 
 def test_config5_properties_at_10M_blocks(genomewide):
-    sc, jobs, total, blocks = genomewide
+    sc, jobs, total, blocks, _ = genomewide
     assert total >= 10_000_000 and len(jobs) > 1_000_000
     g, l = sc.score(jobs, total, blocks)
     g2, l2 = sc.score(jobs, total, blocks)
@@ -81,7 +81,7 @@ def test_config5_compact_worklist_in_slices(genomewide):
     """gat_score_compact at 10 M blocks: the list crosses PCIe in slices that are expanded and scored while the next one is
     copied; the scores are those of gat_score on the same (split) list."""
     from genomealignmenttools_b200.records import pack_compact, split_long_blocks
-    sc, jobs, total, blocks = genomewide
+    sc, jobs, total, blocks, _ = genomewide
     sj, st, sb = split_long_blocks(jobs, total, blocks, 4096)
     g, l = sc.score(sj, st, sb)
     g0, l0 = sc.score(jobs, total, blocks)
@@ -92,6 +92,41 @@ def test_config5_compact_worklist_in_slices(genomewide):
     assert np.array_equal(g, cg) and np.array_equal(l, cl)
     cg, cl = sc.score_compact(cj, cb, ab, an)                                  # again: buffers and streams are reused
     assert np.array_equal(g, cg) and np.array_equal(l, cl)
+
+
+def _subset(g, names, pick):
+    """A PackedGenome holding only the sequences `pick` of g (the oracle unpacks whole chromosomes: keep it to the two needed)."""
+    chunks, offs, cur = [], [], 0
+    for i in pick:
+        nb = (int(g.sizes[i]) + 3) // 4
+        chunks.append(g.packed[int(g.byte_offsets[i]):int(g.byte_offsets[i]) + nb]); offs.append(cur); cur += nb
+    runs = g.n_runs[np.isin(g.n_runs["seq"], pick)].copy()
+    remap = {old: new for new, old in enumerate(pick)}
+    runs["seq"] = [remap[int(x)] for x in runs["seq"]]
+    return PackedGenome([names[i] for i in pick], g.sizes[pick], np.concatenate(chunks), offs, runs)
+
+
+def test_config5_largest_chains_against_the_oracle(genomewide, oracle, tmp_path):
+    """The chains that the sampled reference run of bench.py never reaches: the 10^6-block chain of config 5 (a tenth of all
+    blocks, thousands of chunks, finished by the fix-up kernel) and the next largest ones, scored by the oracle (pinned against
+    the unmodified reference in test_oracle.py) on .2bit files holding just their chromosomes."""
+    sc, jobs, total, blocks, (t, q, tn, qn) = genomewide
+    g, l = sc.score(jobs, total, blocks)
+    counts = job_block_counts(jobs, total)
+    order = np.argsort(-counts)
+    assert counts[order[0]] >= 900_000
+    osc = oracle.scoring(None, "medium")
+    for j in order[:3]:
+        ti, qi = int(jobs["tSeq"][j]), int(jobs["qSeq"][j] & 0x7FFFFFFF)
+        d = tmp_path / ("chain%d" % j)
+        d.mkdir()
+        st, sq = _subset(t, tn, [ti]), _subset(q, qn, [qi])
+        one = jobs[j:j + 1].copy()
+        one["tSeq"] = 0; one["qSeq"] = (one["qSeq"] & np.uint32(0x80000000)); one["blockPtr"] = 0
+        w = synth.Workload(st, sq, one, int(counts[j]), blocks)
+        paths = helpers.write_genomes(w, d)
+        og, ol, _ = oracle.score_jobs(osc, oracle.genome(paths["t"]), oracle.genome(paths["q"]), one, int(counts[j]), blocks)
+        assert (int(g[j]), int(l[j])) == (int(og[0]), int(ol[0])), (j, int(counts[j]))
 
 
 def test_config4_danrer10_chain_real_sizes(oracle, golden, tmp_path):

@@ -448,3 +448,54 @@ def test_chain_split_into_pieces_joins_to_the_unsplit_scores(oracle, tmp_path, p
         tuples = {int(p): tup[k] for k, p in enumerate(part_ix)}
         jg, jl = sharding.join_pieces(w.jobs, w.total, w.blocks, pj, origin, first_piece, g, l, tuples, scoring.gap.cost)
         assert np.array_equal(jg, og) and np.array_equal(jl, ol)
+
+
+GAP_SMALL30 = """tableSize 9
+smallSize 30
+position 1 2 3 11 30 111 2111 12111 32111
+qGap 325 360 400 450 600 900 2900 22900 57900
+tGap 325 360 400 450 600 900 2900 22900 57900
+bothGap 625 660 700 750 900 1400 4900 37900 97900
+"""
+# last knot beyond 2^22: the dense device table stops at 2^22, gaps between there and the knot take the exact routine
+GAP_FAR_KNOT = """tableSize 12
+smallSize 111
+position 1 2 3 11 111 2111 12111 32111 72111 152111 252111 5000000
+qGap 350 425 450 600 900 2900 22900 57900 117900 217900 317900 4317900
+tGap 350 425 450 600 900 2900 22900 57900 117900 217900 317900 4317901
+bothGap 750 825 850 1000 1300 3300 23300 58300 118300 218300 318300 6318300
+"""
+
+
+@pytest.mark.parametrize("name,text", [("small30", GAP_SMALL30), ("far_knot", GAP_FAR_KNOT)])
+def test_custom_linear_gap_files_on_the_device(oracle, kentref, tmp_path, name, text):
+    """-linearGap=<file> with smallSize != 111 and with a last knot beyond the dense table (gat_capi.cu: denseSize is capped at
+    2^22): gap costs evaluated on the device (gat_gap_cost, the routines of the scoring kernel) and whole chains scored
+    with them match the oracle and, where it is built, the unmodified reference's gapCalcCost."""
+    gap_file = str(tmp_path / (name + ".gap"))
+    open(gap_file, "w").write(text)
+    t_names, q_names = ["chrA"], ["chrX"]
+    w = synth.make_workload(t_names, [12_000_000], q_names, [11_000_000], 4000, seed=41, telomere_n=500, n_fraction=0.01,
+                            max_chain_blocks=300, gap_mu=6.0, gap_sigma=3.5, max_gap=6_000_000)
+    paths = helpers.write_case(w, t_names, q_names, str(tmp_path))
+    sc = oracle.scoring(None, gap_file)
+    rng = np.random.default_rng(8)
+    dq = np.concatenate([np.arange(0, 140), rng.integers(0, 9_000_000, 3000), [29, 30, 31, 110, 111, 112, 4194303, 4194304, 4194305,
+                                                                                  4999999, 5000000, 5000001, 2147483647, -5]])
+    dt = np.concatenate([np.zeros(140, dtype=np.int64), rng.integers(0, 3, 3000) * rng.integers(0, 4_000_000, 3000), np.zeros(14, dtype=np.int64)])
+    dq, dt = np.concatenate([dq, dt]), np.concatenate([dt, dq])
+    want = np.array([oracle.lib.orc_gap_cost(sc, int(a), int(b)) for a, b in zip(dq, dt)], dtype=np.int64)
+    if kentref is not None:
+        kentref.set_scoring(None, gap_file)
+        live = np.array([kentref.lib.ref_gap_cost(int(a), int(b)) for a, b in zip(dq, dt)], dtype=np.int64)
+        ok = (dq.astype(np.int64) + dt.astype(np.int64)) < 2 ** 31          # dq + dt overflowing int is undefined in the reference
+        assert np.array_equal(want[ok], live[ok])
+    scoring = Scoring(None, GapCalc.from_file(gap_file))
+    with ChainScorer(0) as s:
+        s.load_genome("t", w.t); s.load_genome("q", w.q); s.set_scoring(scoring)
+        got = s.gap_cost(dq, dt)
+        ok = (dq.astype(np.int64) + dt.astype(np.int64)) < 2 ** 31
+        assert np.array_equal(got[ok].astype(np.int64), want[ok])
+        g, l = s.score(w.jobs, w.total, w.blocks)
+    og, ol, _ = oracle.score_jobs(sc, oracle.genome(paths["t"]), oracle.genome(paths["q"]), w.jobs, w.total, w.blocks)
+    assert np.array_equal(g, og) and np.array_equal(l, ol)
