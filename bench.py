@@ -313,6 +313,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--blocks", type=int, default=10_000_000, help="job-blocks per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configuration: 5 = the genome-wide set the metric is quoted on (default); 1-4 = scoreChain chr1, "
+                         "chainNet -rescore fills, chainCleaner sub-chains, distant-species short blocks (tools/bench_configs.py)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the same --blocks set cut N ways (default), weak = N x --blocks")
     ap.add_argument("--cpu-sample-mbp", type=float, default=160.0)
@@ -322,6 +325,10 @@ def main():
     ap.add_argument("--fold", type=int, default=0, help="experiment: fold block coordinates into the first FOLD bases of their sequences (cache-resident genome)")
     ap.add_argument("--split", type=int, default=0, help="cut blocks longer than this into JOINED records (0 = as generated)")
     args = ap.parse_args()
+    if args.config != 5:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        return bench_configs.run(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -107,26 +107,10 @@ static_assert(SM_SLOT % 16 == 0 && SM_GAP % 16 == 0 && SM_SCORE % 16 == 0 && SM_
 
 // read-only global loads as volatile asm: they are issued where they are written (the compiler would sink them to
 // their first use to save registers, which is exactly the latency the schedule wants to overlap)
-#ifndef GAT_LD_FLAVOR
-#define GAT_LD_FLAVOR 0
-#endif
 __device__ __forceinline__ uint2 ldgPair(const uint2 *p)
 {
     uint2 v;
-#if GAT_LD_FLAVOR == 0
     asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-#elif GAT_LD_FLAVOR == 1
-    asm volatile("ld.global.ca.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-#elif GAT_LD_FLAVOR == 2
-    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-#elif GAT_LD_FLAVOR == 3
-    asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-#elif GAT_LD_FLAVOR == 4
-    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
-                 "ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], pol;\n\t}" : "=r"(v.x), "=r"(v.y) : "l"(p));
-#elif GAT_LD_FLAVOR == 5
-    asm volatile("ld.global.nc.L2::128B.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-#endif
     return v;
 }
 __device__ __forceinline__ uint4 ldgQuad(const uint4 *p)
@@ -163,15 +147,6 @@ __device__ __forceinline__ uint32_t keepIfInside(uint32_t nn, uint32_t ts, uint3
     return n;
 }
 template <int N> struct IntC { static constexpr int value = N; };
-#ifndef GAT_PF
-#define GAT_PF 0                // 1: L2 prefetch of the tile's job descriptors, 2: of the next sub-tile's first windows
-#endif
-#ifndef GAT_ROUND_DEPTH
-#define GAT_ROUND_DEPTH 2       // item rounds in flight per warp
-#endif
-#ifndef GAT_INTERLEAVE
-#define GAT_INTERLEAVE 0        // 1: two sub-tiles' loads in flight per warp (costs registers: measured slower at 64-80)
-#endif
 // a sub-tile between "loads issued" and "loads consumed"
 struct Front {
     uint2 ta, tb, qa, qb, tnw, qnw;
@@ -389,10 +364,6 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         uint32_t jobC = lds(sm + SM_RANK) + __popc(hwC & leMask);
         // (the descriptor array has slack behind it: lanes without a block read whatever index they compute)
         uint4 infoN = ldgQuad(reinterpret_cast<const uint4 *>(P.info + jobC));
-#if GAT_PF & 1
-        // the tile's job descriptors (consecutive jobs, 32 bytes each): ask L2 for them now, 4 jobs per lane
-        prefetchL2(P.info + (__shfl_sync(FULL, jobC, 0) + 4u * (uint32_t)lane));
-#endif
 
         auto front = [&](auto subC) -> Front {
             constexpr int sub = decltype(subC)::value;
@@ -472,16 +443,6 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             }
             itemBase += __shfl_sync(FULL, inc, 31);
             nSlots += __popc(lb);
-#if GAT_PF & 2
-            if (sub + 1 < BPT) {        // ask L2 for the lines of the next sub-tile's first windows (its job descriptor is here by now)
-                const uint32_t nts = lds(recA + 384u * (sub + 1)), nqs = lds(recA + 384u * (sub + 1) + 4);
-                const uint32_t ptw = infoN.x + (nts >> 5), pqw = infoN.y + (nqs >> 5);
-                if (v + 32 < nLive) {
-                    prefetchL2(tPlanes + (ptw < P.t.words ? ptw : 0u));
-                    prefetchL2(qPlanes + (pqw < P.q.words ? pqw : 0u));
-                }
-            }
-#endif
             // first 32 bases
             const uint32_t tSh = F.misc, qSh = F.misc >> 5;
             const uint32_t t1 = __funnelshift_r(F.ta.x, F.tb.x, tSh), t0 = __funnelshift_r(F.ta.y, F.tb.y, tSh);
@@ -502,21 +463,10 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             seen |= (mayN ? 1u : 0u) | ((n > P.smallBases) | ((uint32_t)(F.gap + (1 << 19)) >= (1u << 20)) ? 2u : 0u);
         };
 
-#if GAT_INTERLEAVE
-        Front Fa = front(IntC<0>());
-        Front Fb = front(IntC<1>());
-        back(IntC<0>(), Fa);
-        Fa = front(IntC<2>());
-        back(IntC<1>(), Fb);
-        Fb = front(IntC<3>());
-        back(IntC<2>(), Fa);
-        back(IntC<3>(), Fb);
-#else
         { const Front F = front(IntC<0>()); back(IntC<0>(), F); }
         { const Front F = front(IntC<1>()); back(IntC<1>(), F); }
         { const Front F = front(IntC<2>()); back(IntC<2>(), F); }
         { const Front F = front(IntC<3>()); back(IntC<3>(), F); }
-#endif
     }
     const bool anyN = __any_sync(FULL, (seen & 1u) != 0u), small = !__any_sync(FULL, (seen & 2u) != 0u);
     __syncwarp();
@@ -561,17 +511,11 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
                 }                                                                                           \
             }                                                                                               \
             int x = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, __popc(vmask));                         \
+            /* item scores leave the loop as a running prefix sum stored at each slot's last item (END) */  \
             x = scanStep(x, 1); x = scanStep(x, 2); x = scanStep(x, 4); x = scanStep(x, 8); x = scanStep(x, 16); \
             if ((uint32_t)(LEFT - 1) < 32u) sts(sm + SM_END + 4u * (uint32_t)OW, (uint32_t)(sRun + x));     \
             sRun += __shfl_sync(FULL, x, 31);                                                               \
         }
-#if GAT_ROUND_DEPTH == 1
-        for (int r = 0; r < nRounds; r++) {
-            int oA, lA; uint32_t mA; uint2 a0, a1, a2, a3;
-            GAT_FETCH(r, oA, lA, mA, a0, a1, a2, a3)
-            GAT_CONSUME(r, oA, lA, mA, a0, a1, a2, a3)
-        }
-#elif GAT_ROUND_DEPTH == 2
         int oA, lA, oB, lB; uint32_t mA, mB; uint2 a0, a1, a2, a3, b0, b1, b2, b3;
         GAT_FETCH(0, oA, lA, mA, a0, a1, a2, a3)
         for (int r = 0;; r += 2) {          // software pipeline: round r+1 is in flight while round r is scored
@@ -582,22 +526,6 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             GAT_CONSUME(r + 1, oB, lB, mB, b0, b1, b2, b3)
             if (r + 2 >= nRounds) break;
         }
-#else
-        int oA, lA, oB, lB, oC, lC; uint32_t mA, mB, mC; uint2 a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
-        GAT_FETCH(0, oA, lA, mA, a0, a1, a2, a3)
-        if (1 < nRounds) GAT_FETCH(1, oB, lB, mB, b0, b1, b2, b3)
-        for (int r = 0;; r += 3) {          // software pipeline: rounds r+1 and r+2 are in flight while round r is scored
-            if (r + 2 < nRounds) GAT_FETCH(r + 2, oC, lC, mC, c0, c1, c2, c3)
-            GAT_CONSUME(r, oA, lA, mA, a0, a1, a2, a3)
-            if (r + 1 >= nRounds) break;
-            if (r + 3 < nRounds) GAT_FETCH(r + 3, oA, lA, mA, a0, a1, a2, a3)
-            GAT_CONSUME(r + 1, oB, lB, mB, b0, b1, b2, b3)
-            if (r + 2 >= nRounds) break;
-            if (r + 4 < nRounds) GAT_FETCH(r + 4, oB, lB, mB, b0, b1, b2, b3)
-            GAT_CONSUME(r + 2, oC, lC, mC, c0, c1, c2, c3)
-            if (r + 3 >= nRounds) break;
-        }
-#endif
 #undef GAT_FETCH
 #undef GAT_CONSUME
         __syncwarp();

@@ -14,6 +14,7 @@
 #include <queue>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <thread>
 #include <tuple>
 #include <unistd.h>
@@ -332,22 +333,40 @@ void uploadGenome(gat_ctx *ctx, int side, const TwoBitFile &tb, const std::vecto
 // ------------------------------------------------------------------ text helpers
 static std::string slurp(const std::string &path)
 {
-    std::string cmd;
-    FILE *f;
     const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
-    if (gz) {       // linefile.c:40-53: compressed files are read through a decompressor child
-        cmd = "gzip -dc '" + path + "'";
-        if (access(path.c_str(), R_OK) != 0) fail("Couldn't open %s , %s", path.c_str(), strerror(errno));
-        f = popen(cmd.c_str(), "r");
-    } else
-        f = (path == "stdin") ? stdin : fopen(path.c_str(), "rb");
-    if (!f) fail("Couldn't open %s , %s", path.c_str(), strerror(errno));
     std::string text;
     char buf[1 << 16];
+    if (gz) {
+        // linefile.c:40-53: compressed files are read through a decompressor child.  Spawned without a shell (a file name is
+        // data, not a command line) and its exit status is checked: a corrupt or truncated .gz is an error, not a short input.
+        if (access(path.c_str(), R_OK) != 0) fail("Couldn't open %s , %s", path.c_str(), strerror(errno));
+        int fds[2];
+        if (pipe(fds) != 0) fail("pipe failed: %s", strerror(errno));
+        const pid_t child = fork();
+        if (child < 0) fail("fork failed: %s", strerror(errno));
+        if (child == 0) {
+            dup2(fds[1], STDOUT_FILENO);
+            close(fds[0]); close(fds[1]);
+            execlp("gzip", "gzip", "-dc", "--", path.c_str(), (char *)nullptr);
+            _exit(127);
+        }
+        close(fds[1]);
+        ssize_t n;
+        while ((n = read(fds[0], buf, sizeof buf)) > 0 || (n < 0 && errno == EINTR))
+            if (n > 0) text.append(buf, (size_t)n);
+        close(fds[0]);
+        int status = 0;
+        while (waitpid(child, &status, 0) < 0 && errno == EINTR) {}
+        if (!WIFEXITED(status) || WEXITSTATUS(status) != 0)
+            fail("gzip -dc %s failed (%s %d)", path.c_str(), WIFEXITED(status) ? "exit status" : "signal",
+                 WIFEXITED(status) ? WEXITSTATUS(status) : WTERMSIG(status));
+        return text;
+    }
+    FILE *f = (path == "stdin") ? stdin : fopen(path.c_str(), "rb");
+    if (!f) fail("Couldn't open %s , %s", path.c_str(), strerror(errno));
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
-    if (gz) pclose(f);
-    else if (f != stdin) fclose(f);
+    if (f != stdin) fclose(f);
     return text;
 }
 
@@ -1013,6 +1032,9 @@ void MultiGpu::prepare(const TwoBitFile &tbT, const std::vector<int> &useT, cons
 {
     gap_ = gc;
     haveGap_ = true;
+    tNames_.clear(); qNames_.clear();
+    for (int i : useT) tNames_.push_back(tbT.seqs()[i].name);
+    for (int i : useQ) qNames_.push_back(tbQ.seqs()[i].name);
     std::vector<std::string> errors(ctx.size());
     std::vector<std::thread> threads;
     for (size_t g = 0; g < ctx.size(); g++)
@@ -1237,6 +1259,25 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
     local.assign(nJobs, 0);
     lastShards.assign(nGpus, ShardStats());
     if (wl.jobs.empty()) return;
+    if (const char *prefix = getenv("GAT_DUMP_WORKLIST")) {
+        auto put = [&](const std::string &path, const void *p, size_t bytes) {
+            FILE *f = fopen(path.c_str(), "wb");
+            if (!f || (bytes && fwrite(p, 1, bytes, f) != bytes)) fail("cannot write %s", path.c_str());
+            fclose(f);
+        };
+        const std::string base = std::string(prefix) + "." + std::to_string(dumpCount_++);
+        put(base + ".jobs", wl.jobs.data(), wl.jobs.size() * sizeof(gat_job));
+        put(base + ".blocks", wl.blocks.data(), wl.blocks.size() * sizeof(gat_block));
+        const std::string meta = "{\"jobs\": " + std::to_string(wl.jobs.size()) + ", \"blocks\": " + std::to_string(wl.blocks.size()) +
+                                 ", \"totalJobBlocks\": " + std::to_string(wl.totalJobBlocks) + "}\n";
+        put(base + ".meta", meta.data(), meta.size());
+        std::string names;
+        for (const auto &n : tNames_) names += n + "\n";
+        put(std::string(prefix) + ".tseqs", names.data(), names.size());
+        names.clear();
+        for (const auto &n : qNames_) names += n + "\n";
+        put(std::string(prefix) + ".qseqs", names.data(), names.size());
+    }
     if (nGpus == 1) {
         CompactWorkList cw;
         lastShards[0].jobs = nJobs; lastShards[0].records = wl.blocks.size();

@@ -168,7 +168,12 @@ struct MultiGpu {
     void score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local);
     struct ShardStats { uint64_t jobs = 0, records = 0, h2dBytes = 0, pieces = 0; bool compact = false; };
     std::vector<ShardStats> lastShards;     // what the last score() sent to each GPU (tests, -verbose)
+    // GAT_DUMP_WORKLIST=<prefix> in the environment: every score() call also writes its work-list to <prefix>.<k>.jobs / .blocks
+    // (raw gat_job / gat_block arrays) and the sequence names in upload order to <prefix>.tseqs / .qseqs, so that bench.py can
+    // time exactly the batches a tool sends (configs 2 and 3 of BASELINE.json)
 private:
+    std::vector<std::string> tNames_, qNames_;
+    int dumpCount_ = 0;
     GapCalc gap_;
     bool haveGap_ = false;
     struct Staging { void *p = nullptr; size_t cap = 0; };

@@ -449,3 +449,25 @@ def test_split_giant_jobs_partitions_the_records():
         assert not (blocks["size"][fb] & np.uint32(BLOCK_JOINED)).any()
     limit = ali_bases(jobs, total, blocks).sum() // 16
     assert ali_bases(pj, total, blocks).max() <= 2 * limit + 1
+
+
+def test_gz_inputs_go_through_gzip_without_a_shell(golden, tmp_path):
+    """linefile.c:40-53 reads .gz through a decompressor child: a quote in the file name is data, and a truncated file is an
+    error (the child's exit status is checked), not a shorter chain set."""
+    import shutil
+    lib = hostlib.load()
+    lib.gathost_chains_read.restype = ctypes.c_void_p
+    lib.gathost_chains_read.argtypes = [ctypes.c_char_p]
+    lib.gathost_chains_count.argtypes = [ctypes.c_void_p]
+    lib.gathost_chains_count.restype = ctypes.c_uint64
+    lib.gathost_last_error.restype = ctypes.c_char_p
+    src = os.path.join(golden, "synth_small", "in.chain")
+    odd = str(tmp_path / "it's a.chain")
+    shutil.copy(src, odd)
+    subprocess.check_call(["gzip", "-k", odd])
+    c = lib.gathost_chains_read((odd + ".gz").encode())
+    assert c and lib.gathost_chains_count(c) == 660
+    cut = str(tmp_path / "cut.chain.gz")
+    open(cut, "wb").write(open(odd + ".gz", "rb").read()[:3000])
+    assert not lib.gathost_chains_read(cut.encode())
+    assert b"gzip -dc" in lib.gathost_last_error() and b"failed" in lib.gathost_last_error()
