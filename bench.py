@@ -432,6 +432,7 @@ def main():
     t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = sc.stats()["kernel_launches"] * args.steps
+    long_streamed = int(sc.stats()["long_streamed"])      # which instantiation the library picked for this list
     part_tuples = sc.request_tuples(part_local) if len(part_local) else None      # (one more, untimed pass when pieces are present)
     if part_tuples is not None:
         wl.run()
@@ -447,17 +448,6 @@ def main():
         kms.append(sc.stats()["score_kernel_ms"])
     sc.set_profiling(False)
     kernel_ms = float(np.mean(kms))
-    if os.environ.get("GAT_TIMING"):      # debug build (-DGAT_TIMING): clocks per phase, averaged per warp
-        import ctypes
-        from genomealignmenttools_b200 import _native
-        lib = _native.load()
-        out = (ctypes.c_uint64 * 8)()
-        lib.gat_debug_timing(out)
-        wl.run(); sc.synchronize()
-        lib.gat_debug_timing(out)
-        warps = (w.total + 127) // 128
-        sys.stderr.write("phase clocks per warp: " + " ".join("%d" % (x // warps) for x in out) + "\n")
-
     # ---- end-to-end through the public calls with pinned host buffers (e2e): every step copies the work-list in,
     # runs the kernels and copies the scores out.  Headline: gat_score_compact(), the work-list as a .chain file
     # stores it (size + gaps, 6 bytes per block; expanded on the device).  gat_score() with 12-byte absolute
@@ -593,7 +583,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
-                         "kernel": "scoreTilesKernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "scoreTilesKernel<SYM=1,PLAIN=1,LONG=%d>" % long_streamed, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "algorithmic_bytes": "SURVEY 8d: 0.5 B per aligned bp + 12 B per block + 40 B per job"},
             "clocks": clocks,
             "aligned_bp_per_gpu": w.aligned_bp, "chains_per_gpu": int(len(w.jobs)), "genome_upload_s": round(upload_s, 3),

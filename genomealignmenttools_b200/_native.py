@@ -28,7 +28,8 @@ class GatStats(ctypes.Structure):
     _fields_ = [("score_kernel_ms", ctypes.c_float), ("all_kernels_ms", ctypes.c_float),
                 ("h2d_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
-                ("kernel_launches", ctypes.c_uint32), ("chunks", ctypes.c_uint32)]
+                ("kernel_launches", ctypes.c_uint32), ("chunks", ctypes.c_uint32),
+                ("long_streamed", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 _lib = None

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -68,6 +69,8 @@ struct gat_ctx {
     cudaEvent_t ev[6];
     gat_stats stats;
     gat_worklist *scratch = nullptr;   // device buffers of gat_score(), grown on demand and reused
+    void *xoverBuf = nullptr;          // device scratch of gat_crossover(): pairs in, positions and adjustments out
+    size_t xoverCap = 0;
     void *compactBuf = nullptr;        // device staging of gat_score_compact(): jobs, blocks, abs, anchors
     size_t compactCap = 0;
     cudaStream_t copyStream = nullptr; // gat_score_compact(): slices are copied here while earlier ones are scored
@@ -75,7 +78,7 @@ struct gat_ctx {
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
     uint32_t smallBases = 1;
-    bool oldKernel = false;            // GAT_KERNEL=chunks in the environment: the round-1 scoring kernel (A/B measurements)
+    int forceLong = -1;                 // GAT_LONG_BLOCKS=stream / list in the environment at gat_create (tests, measurements): see pickLong
     std::vector<uint32_t> partJobs;    // gat_request_tuples(): jobs of the next scoring call whose tuple the caller wants
     gat_tuple *partOut = nullptr;
 };
@@ -92,6 +95,7 @@ struct gat_worklist {
     bool borrowedBlocks = false;        // blocks belong to another work-list (re-run without empty jobs)
     int plain = -1;                     // 1: whole chains tiling the record array (PLAIN kernel), 0: clips / shared records,
                                         // -1: not known on the host, jobPrepKernel decides (both instantiations are launched)
+    bool streamLong = true;             // LONG instantiation (blocks of more than 1056 bases are streamed, gat_tiles.cuh): pickLong()
     Tup *chunkHead = nullptr, *chunkTail = nullptr;
     int *chunkTailJob = nullptr;
     long long *outGlobal = nullptr, *outLocal = nullptr;
@@ -135,11 +139,12 @@ extern "C" int gat_create(gat_ctx **out, int device, void *stream)
         return fail(GAT_ECUDA, "gat_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
     gat_ctx *ctx = new gat_ctx();
     ctx->device = device;
+    if (const char *e = getenv("GAT_LONG_BLOCKS")) {
+        if (!strcmp(e, "stream")) ctx->forceLong = 1;
+        else if (!strcmp(e, "list")) ctx->forceLong = 0;
+    }
     for (auto &ev : ctx->ev) ev = nullptr;
     memset(&ctx->stats, 0, sizeof ctx->stats);
-    const char *k = getenv("GAT_KERNEL");
-    ctx->oldKernel = k && strcmp(k, "chunks") == 0;
-    if (const char *f = getenv("GAT_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(f));   // experiment: 32 / 64 / 128
     cudaError_t ce = cudaSuccess;
     if (stream) ctx->stream = (cudaStream_t)stream;
     else { ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->ownStream = ce == cudaSuccess; }
@@ -165,6 +170,7 @@ extern "C" void gat_destroy(gat_ctx *ctx)
     ctx->genome[1].release();
     if (ctx->scratch) { freeWorklistBuffers(ctx->scratch); delete ctx->scratch; }
     cudaFree(ctx->compactBuf);
+    cudaFree(ctx->xoverBuf);
     if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); for (auto &e : ctx->sliceEv) cudaEventDestroy(e); }
     cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense); cudaFree(ctx->err);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -383,7 +389,7 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
     ctx->dynSmem = 0;       // the small gap tables are read through L1
     {
         int perSm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, scoreChunksKernel<true>, TPB, ctx->dynSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, scoreTilesKernel<true, true, false>, TPB, ctx->dynSmem));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         ctx->residentCtas = (uint32_t)(perSm > 0 ? perSm : 1) * (uint32_t)sms;
     }
@@ -441,6 +447,24 @@ extern "C" void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl)
     delete wl;
 }
 
+// Which instantiation scores the list: the one that streams long blocks pays about 3 % on short-block lists and gains up
+// to 40 % on long-block ones (gat_tiles.cuh, streamLongBlocks).  A sample of at most 4096 record sizes, evenly spread,
+// decides: stream when blocks of more than 1056 bases hold at least an eighth of the sampled bases.  Both instantiations
+// score every list exactly; this is about speed only.
+template <typename Rec>
+static bool pickLong(const Rec *recs, uint64_t n, uint32_t sizeMask)
+{
+    if (!recs || n == 0) return false;
+    const uint64_t step = n > 4096 ? n / 4096 : 1;
+    uint64_t all = 0, inLong = 0;
+    for (uint64_t i = 0; i < n; i += step) {
+        const uint32_t size = recs[i].size & sizeMask;
+        all += size;
+        if (size > 1056u) inLong += size;
+    }
+    return inLong * 8 >= all && inLong > 0;
+}
+
 static int uploadWorklist(gat_ctx *ctx, gat_worklist *wl, const gat_job *jobs, const gat_block *blocks)
 {
     if (wl->nJobs) CU(cudaMemcpyAsync(wl->jobs, jobs, wl->nJobs * sizeof(gat_job), cudaMemcpyHostToDevice, ctx->stream));
@@ -462,6 +486,7 @@ extern "C" int gat_worklist_create(gat_ctx *ctx, const gat_job *jobs, uint64_t n
         for (uint64_t j = 0; j < nJobs && wl->plain; j++)
             if (jobs[j].firstBlock != jobs[j].blockPtr || jobs[j].clipStart != GAT_NO_CLIP_START || jobs[j].clipEnd != GAT_NO_CLIP_END) wl->plain = 0;
     }
+    if (rc == GAT_OK) wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, 0x7fffffffu);
     if (rc == GAT_OK) rc = uploadWorklist(ctx, wl, jobs, blocks);
     if (rc == GAT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(GAT_ECUDA, "work-list upload failed");
     if (rc != GAT_OK) { gat_worklist_destroy(ctx, wl); return rc; }
@@ -521,26 +546,25 @@ static int launchPrep(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 // chunks [first, first + count)
 // `plain`: 1 / 0 = the list's mode as the host knows it, -1 = jobPrepKernel's verdict decides on the device: both
 // instantiations are launched and the one that does not apply returns at once.
-static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, cudaStream_t st)
+template <bool PLAIN>
+static void launchTiles(gat_ctx *ctx, const ScoreParams &P, uint32_t count, bool streamLong, cudaStream_t st)
+{
+    if (ctx->sym) {
+        if (streamLong) scoreTilesKernel<true, PLAIN, true><<<count, TPB, 0, st>>>(P);
+        else scoreTilesKernel<true, PLAIN, false><<<count, TPB, 0, st>>>(P);
+    } else {
+        if (streamLong) scoreTilesKernel<false, PLAIN, true><<<count, TPB, 0, st>>>(P);
+        else scoreTilesKernel<false, PLAIN, false><<<count, TPB, 0, st>>>(P);
+    }
+}
+
+static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, bool streamLong, cudaStream_t st)
 {
     if (count == 0) return 0;
     P.chunkBase = first;
-    if (ctx->oldKernel) {
-        if (ctx->sym) scoreChunksKernel<true><<<count, TPB, ctx->dynSmem, st>>>(P);
-        else scoreChunksKernel<false><<<count, TPB, ctx->dynSmem, st>>>(P);
-        return 1;
-    }
     int launches = 0;
-    if (plain != 0) {
-        if (ctx->sym) scoreTilesKernel<true, true><<<count, TPB, 0, st>>>(P);
-        else scoreTilesKernel<false, true><<<count, TPB, 0, st>>>(P);
-        launches++;
-    }
-    if (plain <= 0) {
-        if (ctx->sym) scoreTilesKernel<true, false><<<count, TPB, 0, st>>>(P);
-        else scoreTilesKernel<false, false><<<count, TPB, 0, st>>>(P);
-        launches++;
-    }
+    if (plain != 0) { launchTiles<true>(ctx, P, count, streamLong, st); launches++; }
+    if (plain <= 0) { launchTiles<false>(ctx, P, count, streamLong, st); launches++; }
     return launches;
 }
 
@@ -560,6 +584,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     cudaStream_t st = ctx->stream;
     ctx->stats.kernel_launches = 0;
     ctx->stats.chunks = wl->nChunks;
+    ctx->stats.long_streamed = wl->streamLong ? 1u : 0u;
     if (wl->nJobs == 0) return GAT_OK;
     if (wl->nChunks == 0) {     // every job is empty: scores are 0
         CU(cudaMemsetAsync(wl->outGlobal, 0, wl->nJobs * sizeof(long long), st));
@@ -574,7 +599,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     rc = launchPrep(ctx, wl, st);
     if (rc != GAT_OK) return rc;
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, st);
+    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, st);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     launchFixup(ctx, wl, st);
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
@@ -628,6 +653,7 @@ static int rerunWithoutEmptyJobs(gat_ctx *ctx, gat_worklist *wl, int64_t *global
     gat_worklist tmp;
     tmp.borrowedBlocks = true;
     tmp.plain = -1;
+    tmp.streamLong = wl->streamLong;
     int rc = shapeWorklist(ctx, &tmp, kept.size(), wl->totalJobBlocks, wl->nBlocks);
     tmp.blocks = wl->blocks;
     std::vector<int64_t> g(kept.size()), l(kept.size());
@@ -694,6 +720,7 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
     gat_worklist *wl = ctx->scratch;
     int rc = shapeWorklist(ctx, wl, nJobs, totalJobBlocks, nBlocks);
     wl->plain = -1;
+    wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, 0x7fffffffu);
     cudaStream_t st = ctx->stream;
     const bool prof = ctx->profiling;
     if (rc == GAT_OK && prof) cudaEventRecord(ctx->ev[4], st);
@@ -726,6 +753,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     int rc = shapeWorklist(ctx, wl, nJobs, nBlocks, nBlocks);
     if (rc != GAT_OK) return rc;
     wl->plain = 1;              // whole chains by construction
+    wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, GAT_CBLOCK_MAX_SIZE);
     cudaStream_t st = ctx->stream;
     const uint64_t nGroups = (nBlocks + GAT_CGROUP - 1) / GAT_CGROUP;
     auto up8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
@@ -744,6 +772,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     const gat_cabs *dAbs = reinterpret_cast<const gat_cabs *>(base + oAbs), *dAnch = reinterpret_cast<const gat_cabs *>(base + oAnch);
     const bool prof = ctx->profiling;
     ctx->stats.chunks = wl->nChunks;
+    ctx->stats.long_streamed = wl->streamLong ? 1u : 0u;
     // Big lists go over in slices on a copy stream while the slices that have arrived are expanded and scored: a group
     // of GAT_CGROUP records expands on its own and a chunk needs no record beyond its own.  (With profiling on, one
     // slice on one stream, so that the events of gat_get_stats mean what they say.)
@@ -774,7 +803,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
             rc = launchPrep(ctx, wl, st);
             if (rc != GAT_OK) return rc;
             if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, st);
+            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, st);
             if (prof) CU(cudaEventRecord(ctx->ev[2], st));
         } else {
             rc = launchPrep(ctx, wl, st);
@@ -790,7 +819,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                 CU(cudaStreamWaitEvent(st, ctx->sliceEv[s], 0));
                 expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
-                launchScoring(ctx, P, c0, c1 - c0, wl->plain, st);
+                launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, st);
                 sliceLaunches += 2;
             }
             ctx->stats.kernel_launches = sliceLaunches - 2;
@@ -821,10 +850,17 @@ extern "C" int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPai
     if (nPairs == 0) return GAT_OK;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    gat_xpair *dPairs = nullptr;
-    int *dOut = nullptr;
-    CU(cudaMalloc(&dPairs, nPairs * sizeof(gat_xpair)));
-    if (cudaMalloc(&dOut, 2 * nPairs * sizeof(int)) != cudaSuccess) { cudaFree(dPairs); return fail(GAT_ENOMEM, "gat_crossover: out of device memory"); }
+    // scratch of the context, grown on demand and reused: no allocation per call
+    const size_t need = nPairs * sizeof(gat_xpair) + 2 * nPairs * sizeof(int) + 64;
+    if (need > ctx->xoverCap) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(ctx->xoverBuf);
+        ctx->xoverBuf = nullptr; ctx->xoverCap = 0;
+        if (cudaMalloc(&ctx->xoverBuf, need + need / 4) != cudaSuccess) return fail(GAT_ENOMEM, "gat_crossover: out of device memory");
+        ctx->xoverCap = need + need / 4;
+    }
+    gat_xpair *dPairs = static_cast<gat_xpair *>(ctx->xoverBuf);
+    int *dOut = reinterpret_cast<int *>(static_cast<char *>(ctx->xoverBuf) + ((nPairs * sizeof(gat_xpair) + 15) & ~(size_t)15));
     XoverParams P;
     P.pairs = dPairs; P.nPairs = nPairs;
     P.t = ctx->genome[GAT_TARGET].view(); P.q = ctx->genome[GAT_QUERY].view();
@@ -841,7 +877,6 @@ extern "C" int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPai
     if (e != cudaSuccess) rc = fail(GAT_ECUDA, "gat_crossover failed: %s", cudaGetErrorString(e));
     if (rc == GAT_OK) rc = readDeviceError(ctx, &err);
     cudaStreamSynchronize(st);
-    cudaFree(dPairs); cudaFree(dOut);
     if (rc == GAT_OK && err)
         rc = fail(GAT_EWORKLIST, "crossover pairs rejected by the device:%s%s", (err & ERR_SEQ) ? " sequence index out of range;" : "",
                   (err & ERR_COORD) ? " overlap outside its sequence;" : "");
@@ -872,17 +907,6 @@ extern "C" int gat_gap_cost(gat_ctx *ctx, const int32_t *dq, const int32_t *dt, 
 
 extern "C" uint32_t gat_max_record_bases(const gat_ctx *ctx) { return ctx ? ctx->maxBlockBases : 0; }
 
-#ifdef GAT_TIMING
-// debug builds: clocks per phase summed over all warps since the last call
-extern "C" int gat_debug_timing(unsigned long long *out8)
-{
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out8, gat::gTiming, sizeof(unsigned long long) * 8);
-    unsigned long long z[8] = {0};
-    cudaMemcpyToSymbol(gat::gTiming, z, sizeof z);
-    return 0;
-}
-#endif
 
 extern "C" int gat_synchronize(gat_ctx *ctx)
 {

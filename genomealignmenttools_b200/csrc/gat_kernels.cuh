@@ -13,7 +13,7 @@
 // scoring kernel has no strand logic.  A third, separate plane holds N (1 bit/base) and is only read for
 // blocks whose 256-base windows contain N.
 //
-// Work decomposition: the job-blocks of all jobs form one virtual array; a CTA owns CHUNK consecutive
+// Work decomposition (scoreTilesKernel, gat_tiles.cuh): the job-blocks of all jobs form one virtual array; a CTA owns CHUNK consecutive
 // job-blocks, a warp 128 of them.  The first 32 bases of every block are scored lane = block; what is
 // left is expanded into 32-base "items" and the items -- not the blocks -- are dealt to lanes, so a
 // 30 kb block and a 40 bp block cost what their bases cost.  Per-job global and local scores are a
@@ -37,7 +37,7 @@ constexpr int GROUP_BASES = 128;       // sequences start on a 32-byte sector bo
 // Idle lanes of the last item round read up to 31 words beyond (or, on '-', before) the last block of a warp,
 // and funnel shifts read one word past a window: 36 words of slack at both ends of the genome buffers.
 constexpr int PAD_FRONT_GROUPS = 9;
-constexpr int PAD_BACK_GROUPS = 26;     // + 32 * GAT_AHEAD words of read-ahead behind a continued record
+constexpr int PAD_BACK_GROUPS = 26;
 constexpr int NWIN_SHIFT = 8;          // N summary: one bit per 256 bases
 
 constexpr int ERR_SEQ = 1, ERR_BLOCKIDX = 2, ERR_COORD = 4, ERR_TOOLONG = 8, ERR_CSR = 16;
@@ -227,8 +227,6 @@ __global__ void gapBatchKernel(GapView g, const int *__restrict__ small, const i
 }
 
 // ------------------------------------------------------------------ base windows
-__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // 1 << r for r < 32, else 0 (PTX shl clamps the shift amount; C++ << would be undefined)
 __device__ __forceinline__ uint32_t shl1(uint32_t r)
 {
@@ -264,22 +262,6 @@ __device__ __forceinline__ uint32_t loadNWindow(const uint32_t *__restrict__ np,
     return __funnelshift_r(__ldg(np + n), __ldg(np + n + 1), sh);
 }
 
-// do the 32-base words wFirst..wLast touch a 256-base window (8 words) that contains N?
-__device__ __noinline__ bool wordsTouchNLong(const uint32_t *__restrict__ nwin, uint32_t word0, uint32_t word1, uint32_t loMask, uint32_t hiMask)
-{
-    if (__ldg(nwin + word0) & loMask) return true;
-    for (uint32_t word = word0 + 1; word < word1; word++)
-        if (__ldg(nwin + word)) return true;
-    return (__ldg(nwin + word1) & hiMask) != 0;
-}
-__device__ __forceinline__ bool wordsTouchN(const uint32_t *__restrict__ nwin, uint32_t wFirst, uint32_t wLast)
-{
-    const uint32_t w0 = wFirst >> 3, w1 = wLast >> 3;
-    const uint32_t word0 = w0 >> 5, word1 = w1 >> 5;
-    const uint32_t loMask = 0xffffffffu << (w0 & 31), hiMask = 0xffffffffu >> (31 - (w1 & 31));
-    if (word0 == word1) return (__ldg(nwin + word0) & loMask & hiMask) != 0;     // blocks under 8 kb
-    return wordsTouchNLong(nwin, word0, word1, loMask, hiMask);
-}
 // valid-base mask of one 32-base window pair when N may be present (cold)
 __device__ __noinline__ uint32_t nFreeMask(const uint32_t *__restrict__ tn, uint32_t tW, uint32_t tSh,
                                            const uint32_t *__restrict__ qn, uint32_t qW, uint32_t qSh)
@@ -394,26 +376,11 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
     dst[1] = make_uint4((uint32_t)o.clipStart, (uint32_t)o.clipEnd, o.delta, o.blockPtr);
 }
 
-// ------------------------------------------------------------------ the scoring kernel
-// n < 2^20 (GAT_MAX_BLOCK_BASES); misc: tSh | qSh<<5 | continued-by-next-record<<10 | mayN<<11; excl: items of the warp before this block
-struct __align__(16) StageRec { uint32_t tW, qW, nMisc, excl; };
-
+// ------------------------------------------------------------------ pieces of the scoring kernel (gat_tiles.cuh)
 #ifndef GAT_MIN_CTAS
-#define GAT_MIN_CTAS 14
+#define GAT_MIN_CTAS 14     // 72 registers, 28 warps per SM: measured best (16 CTAs at 64 registers rematerialise too much)
 #endif
-#ifndef GAT_P1_UNROLL
-#define GAT_P1_UNROLL 1
-#endif
-#ifndef GAT_AHEAD
-#define GAT_AHEAD 2       // item rounds of L2 read-ahead inside long blocks (0 = none)
-#endif
-#ifndef GAT_PREFETCH
-#define GAT_PREFETCH 2      // bit 1: fetch the next sub-tile's job and record while the current one is processed
-                            // (asking L2 for a block's last sector from the descriptor pass was measured: no gain)
-#endif
-constexpr int P1_UNROLL = GAT_P1_UNROLL;   // sub-tiles of phase 1 in flight per warp
 constexpr int TILE = 32 * BPT;             // job-blocks per warp
-constexpr int PASS_ITEMS = 1024;           // items covered by one register-resident head bitmap (32 rounds)
 
 __device__ __forceinline__ JobInfo loadInfo(const JobInfo *__restrict__ info, uint32_t j)
 {
@@ -424,20 +391,6 @@ __device__ __forceinline__ JobInfo loadInfo(const JobInfo *__restrict__ info, ui
     r.clipStart = (int)b.x; r.clipEnd = (int)b.y; r.delta = b.z; r.blockPtr = b.w;
     return r;
 }
-
-// chainFastSubsetOnT clip (chain.c:513-522) of one record for one job; te/qe = clipped ends
-__device__ __forceinline__ void clipBlock(const gat_block &b, int clipStart, int clipEnd, int &ts, int &qs, int &len, bool &joined)
-{
-    joined = (b.size & GAT_BLOCK_JOINED) != 0;
-    const int size = (int)(b.size & 0x7fffffffu);
-    ts = b.tStart; qs = b.qStart;
-    int te = ts + size;
-    if (ts < clipStart) { qs += clipStart - ts; ts = clipStart; }
-    if (te > clipEnd) te = clipEnd;
-    len = te - ts;
-}
-
-__device__ __forceinline__ bool isEndOfJob(uint32_t headWord, int lane) { return lane < 31 && ((headWord >> (lane + 1)) & 1u) != 0; }
 
 template <typename T> __device__ __forceinline__ long long finalLocal(const TupT<T> &t)
 {   // a job's running score ends at max(c, d) (entered with 0) and its last peak test is still due
@@ -515,13 +468,6 @@ __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&
     }
 }
 
-#ifdef GAT_TIMING
-__device__ unsigned long long gTiming[8];   // sum over warps of clocks spent per phase (debug builds)
-#define GAT_TICK(i) { const long long now_ = clock64(); if (lane == 0) atomicAdd(&gTiming[i], (unsigned long long)(now_ - tick_)); tick_ = now_; }
-#else
-#define GAT_TICK(i)
-#endif
-
 // the 64-bit form is rare (a warp whose 128 blocks sum past 2^27): keep it out of the hot instruction stream
 __device__ __noinline__ void warpJobReduceWide(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
                                                uint32_t myWr, uint32_t myHw, int warpV0, int vEnd,
@@ -530,336 +476,6 @@ __device__ __noinline__ void warpJobReduceWide(const ScoreParams &P, const int (
 {
     warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane, sWarpAgg, sWarpPend, sWarpHead,
                              sWarpPendJob, sLastIsEnd, sLastJob);
-}
-
-template <bool SYM>
-__global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
-scoreChunksKernel(const __grid_constant__ ScoreParams P)
-{
-#ifdef GAT_TIMING
-    long long tick_ = clock64();
-#endif
-    __shared__ __align__(16) int sGap[CHUNK];   // cost of the gap in front of the block
-    __shared__ __align__(16) int sScore[CHUNK]; // block score: first 32 bases from phase 1, the rest added after phase 2
-    __shared__ __align__(16) int sEnd[CHUNK];   // per list slot: running item-score sum of the warp at the slot's last item (mod 2^32)
-    __shared__ __align__(16) uint32_t sEx[CHUNK];   // per list slot: its item count, then the items of the warp's list in front of it
-    __shared__ __align__(4) unsigned char sSlotV[CHUNK];   // per list slot: its block (index inside the warp's tile)
-    __shared__ __align__(4) unsigned char sFlag[CHUNK];   // 1 head of job, 2 end of job, 4 continues the previous record, 8 valid, 16|32 gap table
-    __shared__ StageRec sStage[WARPS][TILE];    // per warp: its blocks' windows, then its item list
-    __shared__ uint32_t sBits[WARPS][32];       // scratch for the item-head bitmap of a pass
-    __shared__ Tup sWarpAgg[WARPS], sWarpPend[WARPS];
-    __shared__ int sWarpHead[WARPS], sWarpPendJob[WARPS];
-    __shared__ int sArrived, sLastIsEnd;
-    __shared__ uint32_t sLastJob;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sArrived = 0;
-    __syncthreads();                    // the only CTA-wide barrier: from here on warps run on their own
-    // ---- phase 0 (per warp, three independent loads): the chunk's 32 words of the job-start bitmap
-    // (jobPrepKernel), the job that owns the chunk's first block, the rejection flag.
-    const uint32_t chunk = blockIdx.x + P.chunkBase;                 // a launch may cover a slice of the chunks
-    const uint32_t vb0 = chunk * (uint32_t)CHUNK;                    // totalJobBlocks < 2^32
-    const uint32_t total = (uint32_t)P.totalJobBlocks;
-    const int vEnd = (int)(total - vb0 < (uint32_t)CHUNK ? total - vb0 : (uint32_t)CHUNK);   // valid job-blocks of this chunk
-    constexpr int WORDS = CHUNK / 32;   // bitmap words per chunk (<= 32: one per lane; lanes past it see the next chunk's words)
-    const uint32_t myHeadWord = __ldg(P.headBits + (size_t)chunk * WORDS + lane);
-    const uint32_t nextHead0 = __ldg(P.headBits + (size_t)(chunk + 1) * (CHUNK / 32)) & 1u;
-    const uint32_t j0 = __ldg(P.chunkJob + chunk);
-    if (*reinterpret_cast<volatile const int *>(P.err)) return;     // jobPrepKernel rejected the work-list (or met an empty job)
-    uint32_t wrank;     // lane i: jobs that start in words 0..i-1 of the chunk, not counting the chunk's first block
-    {
-        const uint32_t pc = lane < WORDS ? __popc(lane == 0 ? myHeadWord & ~1u : myHeadWord) : 0u;
-        uint32_t inc = pc;
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o = __shfl_up_sync(FULL, inc, off);
-            if (lane >= off) inc += o;
-        }
-        wrank = j0 + inc - pc;          // + j0: the job of block v is wrank(word) + starts in (word start, v], first block excluded
-    }
-    const int *gSmall = P.gapSmall, *gLongPos = P.gapLongPos;       // L1-resident tables (gapCalc.c:12-37)
-    const double *gLongVal = P.gapLongVal;
-
-    GAT_TICK(0)
-    // ---- phase 1: this warp's TILE job-blocks, 32 at a time; block v = warp*TILE + sub*32 + lane.
-    // Pass A1 puts the record loads of all four sub-tiles in flight at once (one DRAM round trip per warp,
-    // not four); pass A2 turns records into window descriptors and asks L2 for the first and last sector of
-    // every window; pass B then scores each block's first 32 bases out of L2 and builds the item list.
-    bool anyN = false;
-    bool anyLong = false;               // some block of this warp is worth reading ahead for
-    int nSlots = 0;                     // blocks of this warp with more than 32 bases: they get a slot in the item list
-    const uint32_t leMask = 0xffffffffu >> (31 - lane);
-    {
-        int carryTe = 0, carryQe = 0;   // clipped ends of the previous sub-tile's last block
-        int errAcc = 0;
-        // job and record of a sub-tile are fetched while the sub-tile before it is being processed
-        auto fetchRecord = [&](int sub, JobInfo &job, gat_block &rec, uint32_t &bi, bool &ok) {
-            const int wi = warp * BPT + sub;
-            const int v = wi * 32 + lane;
-            const uint32_t hw = __shfl_sync(FULL, myHeadWord, wi) & (wi == 0 ? ~1u : ~0u);
-            const uint32_t wr = __shfl_sync(FULL, wrank, wi);
-            const bool valid = v < vEnd;
-            job = loadInfo(P.info, valid ? wr + __popc(hw & leMask) : j0);
-            bi = vb0 + (uint32_t)v + job.delta;
-            ok = valid && (unsigned long long)bi < P.nBlocks;
-            errAcc |= valid && !ok ? ERR_BLOCKIDX : 0;
-            rec = loadBlock(P.blocks, ok ? bi : 0u);
-        };
-#if GAT_PREFETCH & 2
-        JobInfo jobN; gat_block recN; uint32_t biN; bool okN;
-        fetchRecord(0, jobN, recN, biN, okN);
-#endif
-#pragma unroll P1_UNROLL
-        for (int sub = 0; sub < BPT; sub++) {
-            const int wi = warp * BPT + sub;
-            const int v = wi * 32 + lane;
-            const uint32_t hw = __shfl_sync(FULL, myHeadWord, wi);
-            const uint32_t hwn = wi + 1 < 32 ? __shfl_sync(FULL, myHeadWord, (wi + 1) & 31) : nextHead0   /* WORDS < 32: lane WORDS holds the next chunk's first word */;
-#if GAT_PREFETCH & 2
-            const JobInfo job = jobN;
-            const gat_block rec = recN;
-            const uint32_t bi = biN;
-            const bool ok = okN;
-            if (sub + 1 < BPT) fetchRecord(sub + 1, jobN, recN, biN, okN);
-#else
-            JobInfo job; gat_block rec; uint32_t bi; bool ok;
-            fetchRecord(sub, job, rec, bi, ok);
-#endif
-            const bool isHead = ((hw >> lane) & 1u) != 0;
-            const bool isEnd = ((lane < 31 ? hw >> (lane + 1) : hwn) & 1u) != 0;
-            uint32_t flag = v < vEnd ? (8u | (isHead ? 1u : 0u) | (isEnd ? 2u : 0u)) : 0u;
-            // chainFastSubsetOnT clip (chain.c:513-522)
-            const bool joined = (rec.size & GAT_BLOCK_JOINED) != 0;
-            // is the record after mine its continuation (a long block cut by the host)?  Then the genome words behind
-            // my window are the next record's: the item loop may read ahead past my end.  (Lane 31 does not know.)
-            bool continued = false;
-            if (__any_sync(FULL, ok && joined))        // split blocks are rare: most sub-tiles skip this
-                continued = __shfl_down_sync(FULL, (int)(ok && joined), 1) != 0 && lane < 31 && !isEndOfJob(hw, lane);
-            int ts = rec.tStart, qs = rec.qStart;
-            int te = ts + (int)(rec.size & 0x7fffffffu);
-            const int cut = job.clipStart > ts ? job.clipStart - ts : 0;
-            ts += cut; qs += cut;
-            te = te > job.clipEnd ? job.clipEnd : te;
-            const int len = te - ts;
-            const int nn = len > 0 ? len : 0;
-            const bool bad = nn > 0 && (ts < 0 || qs < 0 || (unsigned)ts + (unsigned)nn > job.tSize || (unsigned)qs + (unsigned)nn > job.qSize);
-            const bool tooLong = (uint32_t)nn > P.maxBlockBases;
-            errAcc |= ok && bad ? ERR_COORD : 0;
-            errAcc |= ok && !bad && tooLong ? ERR_TOOLONG : 0;
-            // a '-' job points at the reverse-complement copy of its query sequence, whose coordinates
-            // are the chain's own (chainFormat.doc): both strands read forward from here on
-            const uint32_t n = ok && !bad && !tooLong ? (uint32_t)nn : 0u;
-            const uint32_t tW = n ? job.tBaseW + ((uint32_t)ts >> 5) : 0u;
-            const uint32_t qW = n ? job.qBaseW + ((uint32_t)qs >> 5) : 0u;
-            const uint32_t tSh = (uint32_t)ts & 31u, qSh = (uint32_t)qs & 31u;
-            // the block's first 32 bases are scored right here (lane = block, no item bookkeeping); blocks
-            // without bases read the front padding
-            const uint2 ta = __ldg(P.t.planes + tW), tb = __ldg(P.t.planes + tW + 1);
-            const uint2 qa = __ldg(P.q.planes + qW), qb = __ldg(P.q.planes + qW + 1);
-            bool mayN = false;
-            if (n) mayN = wordsTouchN(P.t.nwin, tW, tW + ((tSh + n - 1) >> 5)) || wordsTouchN(P.q.nwin, qW, qW + ((qSh + n - 1) >> 5));
-            // the block in front of mine (same job): lane-1 holds it; lane 0 takes the previous sub-tile's
-            // last block, or the record fetched for that purpose when this is the warp's first sub-tile
-            const int cte = ok ? te : 0, cqe = ok ? qs + len : 0;
-            int pte = __shfl_up_sync(FULL, cte, 1), pqe = __shfl_up_sync(FULL, cqe, 1);
-            if (sub == 0 && lane == 0 && ok && !isHead && bi > 0) {     // the record in front of the warp's first block
-                int pts, pqs, plen; bool pj;
-                clipBlock(loadBlock(P.blocks, bi - 1), job.clipStart, job.clipEnd, pts, pqs, plen, pj);
-                carryTe = pts + plen; carryQe = pqs + plen;
-            }
-            pte = lane == 0 ? carryTe : pte; pqe = lane == 0 ? carryQe : pqe;
-            carryTe = __shfl_sync(FULL, cte, 31); carryQe = __shfl_sync(FULL, cqe, 31);
-            // gap in front of the block (gapCalcCost, gapCalc.c:298-331)
-            int gap = 0;
-            if (ok && !isHead) {
-                if (joined) flag |= 4u;
-                else gap = gapCost(P.gap, gSmall, P.gapDense, gLongPos, gLongVal, qs - pqe, ts - pte);
-            }
-            sGap[v] = gap;
-            sFlag[v] = (unsigned char)flag;
-            const uint32_t t1 = __funnelshift_r(ta.x, tb.x, tSh), t0 = __funnelshift_r(ta.y, tb.y, tSh);
-            const uint32_t q1 = __funnelshift_r(qa.x, qb.x, qSh), q0 = __funnelshift_r(qa.y, qb.y, qSh);
-            int nv = n >= 32 ? 32 : (int)n;
-            uint32_t vmask = shrOnes(32u - (uint32_t)nv);
-            if (mayN) {
-                vmask &= nFreeMask(P.t.nplane, tW, tSh, P.q.nplane, qW, qSh);
-                nv = __popc(vmask);
-            }
-            sScore[v] = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);
-            anyN |= mayN;
-            anyLong |= continued || n > 1024u * GAT_AHEAD;
-            // what is left of the block joins the warp's item list
-            const bool listed = n > 32;
-            const uint32_t lb = __ballot_sync(FULL, listed);
-            if (listed) {
-                const int slot = nSlots + __popc(lb & (leMask >> 1));
-                sStage[warp][slot] = StageRec{tW + 1, qW + 1, (n - 32) | ((tSh | (qSh << 5) | (continued ? 0x400u : 0u) | (mayN ? 0x800u : 0u)) << 20), 0u};
-                sEx[warp * TILE + slot] = (n - 1) >> 5;             // item count for now
-                sSlotV[warp * TILE + slot] = (unsigned char)(sub * 32 + lane);
-            }
-            nSlots += __popc(lb);
-        }
-        if (errAcc) atomicOr(P.err, errAcc);
-    }
-    anyN = __any_sync(FULL, anyN);
-    anyLong = __any_sync(FULL, anyLong);
-    GAT_TICK(1)
-
-    // ---- phase 2: what is left of the warp's blocks as one list of 32-base items, dealt to lanes round
-    // by round (adjacent lanes = adjacent items: coalesced).  Lane l speaks for list slots 4l..4l+3 when the
-    // item prefix is built.  Per pass of 1024 items the bit "this list position starts a block" lives in
-    // one register per lane (lane r: round r), so the owner of an item is one shuffle and two popcounts.
-    // Scores leave the loop as a running prefix sum stored at each slot's last item: no atomics.
-    const int warpV0 = warp * TILE;
-    if (nSlots) {
-        uint32_t totalItems;
-        uint4 *exMine = reinterpret_cast<uint4 *>(&sEx[warpV0 + BPT * lane]);      // my four slots: one 16-byte access, no bank conflicts
-        {
-            uint4 ex;
-            __syncwarp();
-            const uint4 c = *exMine;
-            const uint32_t c0 = BPT * lane + 0 < nSlots ? c.x : 0u, c1 = BPT * lane + 1 < nSlots ? c.y : 0u;
-            const uint32_t c2 = BPT * lane + 2 < nSlots ? c.z : 0u, c3 = BPT * lane + 3 < nSlots ? c.w : 0u;
-            uint32_t incl = c0 + c1 + c2 + c3;
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, incl, off);
-                if (lane >= off) incl += o;
-            }
-            totalItems = __shfl_sync(FULL, incl, 31);
-            ex.x = incl - (c0 + c1 + c2 + c3); ex.y = ex.x + c0; ex.z = ex.y + c1; ex.w = ex.z + c2;
-            *exMine = ex;               // slots past the list get totalItems: they never own an item
-            __syncwarp();
-        }
-        uint32_t *bits = sBits[warp];
-        const uint2 *__restrict__ tPlanes = P.t.planes, *__restrict__ qPlanes = P.q.planes;
-        int before = 0;                         // list slots that start before the round being fetched
-        int sRun = 0;                           // sum of all item scores of earlier rounds (mod 2^32)
-        for (uint32_t passBase = 0; passBase < totalItems; passBase += PASS_ITEMS) {
-            bits[lane] = 0;
-            __syncwarp();
-            const uint4 ex = *exMine;
-            { const uint32_t e = ex.x - passBase; if (BPT * lane + 0 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
-            { const uint32_t e = ex.y - passBase; if (BPT * lane + 1 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
-            { const uint32_t e = ex.z - passBase; if (BPT * lane + 2 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
-            { const uint32_t e = ex.w - passBase; if (BPT * lane + 3 < nSlots && e < (uint32_t)PASS_ITEMS) atomicOr(&bits[e >> 5], 1u << (e & 31)); }
-            __syncwarp();
-            const uint32_t myWord = bits[lane];
-            __syncwarp();
-            const uint32_t passItems = totalItems - passBase < (uint32_t)PASS_ITEMS ? totalItems - passBase : (uint32_t)PASS_ITEMS;
-            const int nRounds = (int)((passItems + 31) >> 5);
-            const uint32_t idx0 = passBase + lane;
-            // A round's state: owner slot, bases left in its block from this item on (<= 0: idle lane),
-            // misc, and the four uint2 window halves.  Idle lanes (only in the list's last round) land on the
-            // last slot with left <= 0 and read padding or neighbouring words: harmless, they score 0.
-#define GAT_FETCH(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                        \
-            {                                                                                               \
-                const uint32_t heads = __shfl_sync(FULL, myWord, (R));                                      \
-                OW = before - 1 + __popc(heads & leMask);                                                   \
-                before += __popc(heads);                                                                    \
-                const StageRec rec = sStage[warp][OW];                                                      \
-                const uint32_t k = idx0 + ((uint32_t)(R) << 5) - sEx[warpV0 + OW];                          \
-                MISC = rec.nMisc >> 20;                                                                     \
-                LEFT = (int)(rec.nMisc & 0xfffffu) - (int)(k << 5);                                         \
-                const uint2 *tp = tPlanes + (rec.tW + k);                                                   \
-                const uint2 *qp = qPlanes + (rec.qW + k);                                                   \
-                W0 = __ldg(tp); W1 = __ldg(tp + 1); W2 = __ldg(qp); W3 = __ldg(qp + 1);                     \
-                if (GAT_AHEAD && anyLong && (LEFT > 1024 * GAT_AHEAD || ((MISC & 0x400u) && LEFT > 0))) {   /* a long block (or one that goes on in the next record): ask L2 for the words GAT_AHEAD rounds from now */ \
-                    prefetchL2(tp + 32 * GAT_AHEAD); prefetchL2(qp + 32 * GAT_AHEAD);                       \
-                }                                                                                           \
-            }
-#define GAT_CONSUME(R, OW, LEFT, MISC, W0, W1, W2, W3)                                                      \
-            {                                                                                               \
-                const uint32_t tSh = MISC, qSh = MISC >> 5;                                                 \
-                const uint32_t t1 = __funnelshift_r(W0.x, W1.x, tSh), t0 = __funnelshift_r(W0.y, W1.y, tSh);\
-                const uint32_t q1 = __funnelshift_r(W2.x, W3.x, qSh), q0 = __funnelshift_r(W2.y, W3.y, qSh);\
-                int nv = LEFT > 32 ? 32 : (LEFT < 0 ? 0 : LEFT);                                            \
-                uint32_t vmask = shrOnes(32u - (uint32_t)nv);                                               \
-                if (anyN && (MISC & 0x800u) && nv) {                                                        \
-                    const StageRec rec = sStage[warp][OW];                                                  \
-                    const uint32_t k = idx0 + ((uint32_t)(R) << 5) - sEx[warpV0 + OW];                      \
-                    vmask &= nFreeMask(P.t.nplane, rec.tW + k, tSh, P.q.nplane, rec.qW + k, qSh);           \
-                    nv = __popc(vmask);                                                                     \
-                }                                                                                           \
-                int x = scoreWindow<SYM>(P.coef, t1, t0, q1, q0, vmask, nv);                                \
-                x = scanStep(x, 1); x = scanStep(x, 2); x = scanStep(x, 4); x = scanStep(x, 8); x = scanStep(x, 16); \
-                if ((uint32_t)(LEFT - 1) < 32u) sEnd[warpV0 + OW] = sRun + x;                               \
-                sRun += __shfl_sync(FULL, x, 31);                                                           \
-            }
-            int oA, lA, oB, lB; uint32_t mA, mB; uint2 a0, a1, a2, a3, b0, b1, b2, b3;
-            GAT_FETCH(0, oA, lA, mA, a0, a1, a2, a3)
-            for (int r = 0;; r += 2) {          // software pipeline: round r+1 is in flight while round r is scored
-                if (r + 1 < nRounds) GAT_FETCH(r + 1, oB, lB, mB, b0, b1, b2, b3)
-                GAT_CONSUME(r, oA, lA, mA, a0, a1, a2, a3)
-                if (r + 1 >= nRounds) break;
-                if (r + 2 < nRounds) GAT_FETCH(r + 2, oA, lA, mA, a0, a1, a2, a3)
-                GAT_CONSUME(r + 1, oB, lB, mB, b0, b1, b2, b3)
-                if (r + 2 >= nRounds) break;
-            }
-#undef GAT_FETCH
-#undef GAT_CONSUME
-        }
-        __syncwarp();
-        // a slot's items summed to sEnd[slot] - sEnd[slot - 1]: add that to its block's score
-        {
-            const int4 e4 = *reinterpret_cast<const int4 *>(&sEnd[warpV0 + BPT * lane]);
-            int prevEnd = __shfl_up_sync(FULL, e4.w, 1);
-            if (lane == 0) prevEnd = 0;
-            const int d[BPT] = {e4.x - prevEnd, e4.y - e4.x, e4.z - e4.y, e4.w - e4.z};
-            const uint32_t v4 = *reinterpret_cast<const uint32_t *>(&sSlotV[warpV0 + BPT * lane]);
-#pragma unroll
-            for (int k = 0; k < BPT; k++)
-                if (BPT * lane + k < nSlots) sScore[warpV0 + ((v4 >> (8 * k)) & 0xffu)] += d[k];
-        }
-    }
-    __syncwarp();
-    GAT_TICK(2)
-
-    // ---- phase 3: ordered segmented reduction of tuples, per warp: lane l walks job-blocks 4l..4l+3
-    // of the warp, one warp scan joins the lanes; what crosses warps is resolved by whichever warp
-    // of the CTA finishes last (no CTA-wide barrier: warps retire at their own pace).
-    {
-        const int4 a4 = *reinterpret_cast<const int4 *>(&sScore[warpV0 + BPT * lane]);
-        const int4 g4 = *reinterpret_cast<const int4 *>(&sGap[warpV0 + BPT * lane]);
-        const uint32_t fl4 = *reinterpret_cast<const uint32_t *>(&sFlag[warpV0 + BPT * lane]);
-        const int a[BPT] = {a4.x, a4.y, a4.z, a4.w};
-        const int g[BPT] = {g4.x, g4.y, g4.z, g4.w};
-        // 32-bit tuples if every partial sum of this warp's blocks stays below 2^27
-        long long mag = 0;
-#pragma unroll
-        for (int k = 0; k < BPT; k++) mag += (long long)(a[k] < 0 ? -(long long)a[k] : (long long)a[k]) + (g[k] < 0 ? -(long long)g[k] : (long long)g[k]);
-        const bool small = __all_sync(FULL, mag < (1LL << 22));
-        const int wsel = warp * BPT + (lane >> 3);          // bitmap word of my four blocks
-        const uint32_t myWr = __shfl_sync(FULL, wrank, wsel), myHw = __shfl_sync(FULL, myHeadWord, wsel) & (wsel == 0 ? ~1u : ~0u);
-        if (small) warpJobReduce<int>(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
-                                      sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
-        else warpJobReduceWide(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
-                               sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
-    }
-    GAT_TICK(3)
-    // last warp of the CTA to get here stitches the warps together
-    __threadfence_block();
-    __syncwarp();
-    int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(&sArrived, 1);
-    arrived = __shfl_sync(FULL, arrived, 0);
-    if (arrived != WARPS - 1 || lane != 0) return;
-    __threadfence_block();
-    Tup c = tupIdentity();
-    bool ch = false;
-    for (int w = 0; w < WARPS; w++) {
-        if (sWarpPendJob[w] >= 0) {
-            const Tup fin = tupCombine(c, sWarpPend[w]);
-            if (ch) {
-                P.outGlobal[sWarpPendJob[w]] = fin.d;
-                P.outLocal[sWarpPendJob[w]] = finalLocal(fin);
-            } else P.chunkHead[chunk] = fin;       // job began in an earlier chunk and ends here
-        }
-        if (sWarpHead[w]) { c = sWarpAgg[w]; ch = true; }
-        else c = tupCombine(c, sWarpAgg[w]);
-    }
-    // the chunk's last valid job-block: does its job run on into the next chunk?
-    if (sLastIsEnd) P.chunkTailJob[chunk] = -1;
-    else if (ch) { P.chunkTail[chunk] = c; P.chunkTailJob[chunk] = (int)sLastJob; }
-    else { P.chunkHead[chunk] = c; P.chunkTailJob[chunk] = -1; }
 }
 
 // ------------------------------------------------------------------ cross-chunk fix-up
@@ -1120,10 +736,14 @@ __global__ void expandJobsKernel(const gat_cjob *__restrict__ cj, unsigned long 
 }
 
 // ------------------------------------------------------------------ crossover of overlapping blocks
-// cBlockFindCrossover (kent/src/lib/chainConnect.c:61-105), one thread per pair.  With L[i], R[i] the scores of base i
-// of the overlap in the left / right block, the reference starts from sum(R), adds L[i] - R[i] base by base and keeps
-// the first strictly better position: pos = first argmax of the prefix sums P (0 if none is positive) and
+// cBlockFindCrossover (kent/src/lib/chainConnect.c:61-105).  With L[i], R[i] the scores of base i of the overlap in the
+// left / right block, the reference starts from sum(R), adds L[i] - R[i] base by base and keeps the first strictly better
+// position: pos = first argmax of the prefix sums P (0 if none is positive) and
 // retScoreAdjustment = sum(R) + sum(L) - (sum(R) + max(0, max P)) = sum(L) - max(0, max P).
+// One thread per pair for overlaps of up to XOVER_SHORT bases (what chainRemovePartialOverlaps mostly meets); longer
+// overlaps are taken by the whole warp one after the other, lane = base: prefix sums by a warp scan, the first arg-max of
+// a 32-base word by REDUX.MAX + ballot.
+constexpr int XOVER_SHORT = 64;
 struct XoverParams {
     const gat_xpair *pairs;
     unsigned long long nPairs;
@@ -1139,44 +759,84 @@ __device__ __forceinline__ void xoverWindow(const GenomeView &g, long long base,
     loadWindow(g.planes, w, sh, hi, lo);
     n = loadNWindow(g.nplane, w, sh);
 }
+// score of base b of a window pair: 0 if either side is N (axt.c:431-454)
+__device__ __forceinline__ int xoverScore(const int *matrix, uint32_t q1, uint32_t q0, uint32_t t1, uint32_t t0, uint32_t n, int b)
+{
+    const int code = (int)((((q1 >> b) & 1u) << 3) | (((q0 >> b) & 1u) << 2) | (((t1 >> b) & 1u) << 1) | ((t0 >> b) & 1u));
+    return ((n >> b) & 1u) ? 0 : matrix[code];
+}
 
 __global__ void crossoverKernel(const __grid_constant__ XoverParams P)
 {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.nPairs) return;
-    const gat_xpair p = P.pairs[i];
+    const int lane = threadIdx.x & 31;
+    bool ok = i < P.nPairs;
+    gat_xpair p{0, 0, 0, 0, 0, 0, 0};
+    if (ok) p = P.pairs[i];
     const uint32_t qSeq = p.qSeq & 0x7fffffffu;
-    if (p.tSeq >= P.t.nSeq || qSeq >= P.q.nSeq) { atomicOr(P.err, ERR_SEQ); return; }
-    const long long tSize = P.t.seqSize[p.tSeq], qSize = P.q.seqSize[qSeq], ov = p.overlap;
-    if (ov < 0 || p.leftTEnd - ov < 0 || p.leftQEnd - ov < 0 || p.leftTEnd > tSize || p.leftQEnd > qSize ||
-        p.rightTStart < 0 || p.rightQStart < 0 || p.rightTStart + ov > tSize || p.rightQStart + ov > qSize) {
-        atomicOr(P.err, ERR_COORD);
-        return;
-    }
-    const long long tBase = P.t.seqBase[p.tSeq], qBase = P.q.seqBase[(p.qSeq >> 31) ? P.q.nSeq + qSeq : qSeq];
-    const long long lt = tBase + p.leftTEnd - ov, lq = qBase + p.leftQEnd - ov, rt = tBase + p.rightTStart, rq = qBase + p.rightQStart;
-    long long sumL = 0, prefix = 0, best = 0;
-    int bestPos = 0;
-    for (long long off = 0; off < ov; off += 32) {
-        uint32_t lt1, lt0, ltn, lq1, lq0, lqn, rt1, rt0, rtn, rq1, rq0, rqn;
-        xoverWindow(P.t, lt + off, lt1, lt0, ltn);
-        xoverWindow(P.q, lq + off, lq1, lq0, lqn);
-        xoverWindow(P.t, rt + off, rt1, rt0, rtn);
-        xoverWindow(P.q, rq + off, rq1, rq0, rqn);
-        const uint32_t ln = ltn | lqn, rn = rtn | rqn;        // N on either side scores 0 (axt.c:431-454)
-        const int nb = ov - off < 32 ? (int)(ov - off) : 32;
-        for (int b = 0; b < nb; b++) {
-            const int lcode = (int)((((lq1 >> b) & 1u) << 3) | (((lq0 >> b) & 1u) << 2) | (((lt1 >> b) & 1u) << 1) | ((lt0 >> b) & 1u));
-            const int rcode = (int)((((rq1 >> b) & 1u) << 3) | (((rq0 >> b) & 1u) << 2) | (((rt1 >> b) & 1u) << 1) | ((rt0 >> b) & 1u));
-            const int L = ((ln >> b) & 1u) ? 0 : P.matrix[lcode];
-            const int R = ((rn >> b) & 1u) ? 0 : P.matrix[rcode];
-            sumL += L;
-            prefix += L - R;
-            if (prefix > best) { best = prefix; bestPos = (int)off + b + 1; }
+    long long lt = 0, lq = 0, rt = 0, rq = 0;
+    const long long ov = p.overlap;
+    if (ok) {
+        if (p.tSeq >= P.t.nSeq || qSeq >= P.q.nSeq) { atomicOr(P.err, ERR_SEQ); ok = false; }
+        else {
+            const long long tSize = P.t.seqSize[p.tSeq], qSize = P.q.seqSize[qSeq];
+            if (ov < 0 || p.leftTEnd - ov < 0 || p.leftQEnd - ov < 0 || p.leftTEnd > tSize || p.leftQEnd > qSize ||
+                p.rightTStart < 0 || p.rightQStart < 0 || p.rightTStart + ov > tSize || p.rightQStart + ov > qSize) {
+                atomicOr(P.err, ERR_COORD);
+                ok = false;
+            } else {
+                const long long tBase = P.t.seqBase[p.tSeq], qBase = P.q.seqBase[(p.qSeq >> 31) ? P.q.nSeq + qSeq : qSeq];
+                lt = tBase + p.leftTEnd - ov; lq = qBase + p.leftQEnd - ov; rt = tBase + p.rightTStart; rq = qBase + p.rightQStart;
+            }
         }
     }
-    P.pos[i] = bestPos;
-    P.adjust[i] = (int)(sumL - best);
+    if (ok && ov <= XOVER_SHORT) {      // my own loop
+        long long sumL = 0, prefix = 0, best = 0;
+        int bestPos = 0;
+        for (long long off = 0; off < ov; off += 32) {
+            uint32_t lt1, lt0, ltn, lq1, lq0, lqn, rt1, rt0, rtn, rq1, rq0, rqn;
+            xoverWindow(P.t, lt + off, lt1, lt0, ltn);
+            xoverWindow(P.q, lq + off, lq1, lq0, lqn);
+            xoverWindow(P.t, rt + off, rt1, rt0, rtn);
+            xoverWindow(P.q, rq + off, rq1, rq0, rqn);
+            const int nb = ov - off < 32 ? (int)(ov - off) : 32;
+            for (int b = 0; b < nb; b++) {
+                const int L = xoverScore(P.matrix, lq1, lq0, lt1, lt0, ltn | lqn, b), R = xoverScore(P.matrix, rq1, rq0, rt1, rt0, rtn | rqn, b);
+                sumL += L;
+                prefix += L - R;
+                if (prefix > best) { best = prefix; bestPos = (int)off + b + 1; }
+            }
+        }
+        P.pos[i] = bestPos;
+        P.adjust[i] = (int)(sumL - best);
+    }
+    // long overlaps, one after the other, the warp's lanes = the bases of a 32-base word
+    for (unsigned m = __ballot_sync(FULL, ok && ov > XOVER_SHORT); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const long long wlt = shfl64(lt, src), wlq = shfl64(lq, src), wrt = shfl64(rt, src), wrq = shfl64(rq, src), wov = shfl64(ov, src);
+        long long sumL = 0, base = 0, best = 0;
+        long long bestPos = 0;
+        for (long long off = 0; off < wov; off += 32) {
+            uint32_t lt1, lt0, ltn, lq1, lq0, lqn, rt1, rt0, rtn, rq1, rq0, rqn;
+            xoverWindow(P.t, wlt + off, lt1, lt0, ltn);
+            xoverWindow(P.q, wlq + off, lq1, lq0, lqn);
+            xoverWindow(P.t, wrt + off, rt1, rt0, rtn);
+            xoverWindow(P.q, wrq + off, rq1, rq0, rqn);
+            const bool live = off + lane < wov;
+            const int L = live ? xoverScore(P.matrix, lq1, lq0, lt1, lt0, ltn | lqn, lane) : 0;
+            const int R = live ? xoverScore(P.matrix, rq1, rq0, rt1, rt0, rtn | rqn, lane) : 0;
+            int pre = L - R;
+            pre = scanStep(pre, 1); pre = scanStep(pre, 2); pre = scanStep(pre, 4); pre = scanStep(pre, 8); pre = scanStep(pre, 16);
+            const int wordMax = __reduce_max_sync(FULL, live ? pre : INT32_MIN);
+            if (base + wordMax > best) {        // strictly better: the first position that reaches it
+                best = base + wordMax;
+                bestPos = off + __ffs(__ballot_sync(FULL, live && pre == wordMax));
+            }
+            base += __shfl_sync(FULL, pre, 31);
+            sumL += __reduce_add_sync(FULL, L);
+        }
+        if (lane == src) { P.pos[i] = (int)bestPos; P.adjust[i] = (int)(sumL - best); }
+    }
 }
 
 }  // namespace gat

@@ -19,7 +19,8 @@
 //  * the item-head bitmap is written while the list is built (one shared atomic per listed block);
 //  * one dense gap table (small gaps included) and an N summary stored as overlapping word pairs: one
 //    load and a funnel shift per test, no branches in front of the loads;
-//  * all loads of a sub-tile (genome windows, N summary, gap cost) are issued before any is consumed.
+//  * all loads of a sub-tile (genome windows, N summary, gap cost) are issued before any is consumed;
+//  * blocks of more than 1056 bases are streamed by the whole warp outside the list: no owner search, no scan.
 #pragma once
 #include "gat_kernels.cuh"
 
@@ -100,6 +101,7 @@ constexpr uint32_t SM_GAP = SM_EX + TILE * 4;
 constexpr uint32_t SM_SCORE = SM_GAP + TILE * 4;
 constexpr uint32_t SM_FLAG = SM_SCORE + TILE * 4;
 constexpr uint32_t SM_BAR = SM_FLAG + TILE;
+constexpr uint32_t SM_NLONG = SM_BAR + 8;           // long blocks of this tile (streamLongBlocks)
 constexpr uint32_t SM_HEAD = SM_BAR + 16;            // this warp's 4 words of the job-start bitmap and the one behind them
 constexpr uint32_t SM_RANK = SM_HEAD + 32;           // jobs that start in front of each of the 4 words (+ the chunk's first job)
 constexpr uint32_t SM_WARP_BYTES = SM_RANK + 16;
@@ -146,7 +148,7 @@ __device__ __forceinline__ uint32_t keepIfInside(uint32_t nn, uint32_t ts, uint3
         : "=r"(n) : "r"(nn), "r"(ts), "r"(qs), "r"(tSize), "r"(qSize), "r"(maxBases), "r"((uint32_t)live));
     return n;
 }
-template <int N> struct IntC { static constexpr int value = N; };
+template <int N> struct IntC { static constexpr int value = N; __host__ __device__ constexpr operator int() const { return N; } };
 // a sub-tile between "loads issued" and "loads consumed"
 struct Front {
     uint2 ta, tb, qa, qb, tnw, qnw;
@@ -247,7 +249,57 @@ __device__ __forceinline__ void warpJobReduce32(const ScoreParams &P, const uint
     }
 }
 
-template <bool SYM, bool PLAIN>
+// LONG instantiations: blocks of more than LONG_BASES bases are not listed.  After the item rounds the warp streams them
+// one after the other, lane = word, 1024 bases per step and LONG_STEPS steps (8 loads per lane each) in flight; every lane
+// keeps its own sum and one REDUX per block closes it: no owner search, no scan, no slot look-ups.  Descriptors (words of
+// the block's 33rd base, bases behind the first window, shifts and block index) sit at the far end of the slot array.
+//
+// Why a template parameter and not one kernel: the per-block path (phase 1 unrolled four times) is as large as the SM's
+// instruction cache takes -- with this loop behind it warps wait for instruction fetches (no_instruction 0.22 -> 1.84 per
+// issue, +17 % kernel time at 67-base blocks, profiles/README.md).  So the LONG instantiations run phase 1 as a loop (+3 %
+// at 67-base blocks) and stream long blocks (9-kb blocks: 0.42 -> 0.58 of the HBM roofline); the others list every block as
+// before.  The host picks per work-list from a sample of the block sizes (gat_capi.cu: pickLong).
+constexpr uint32_t LONG_BASES = 32 + 1024;
+constexpr int LONG_STEPS = 2;           // steps (of 1024 bases) a warp keeps in flight per long block
+template <bool SYM>
+__device__ __forceinline__ void streamLongBlocks(const ScoreParams &P, uint32_t sm, int nLong, int lane, bool anyN)
+{
+    const uint2 *__restrict__ tPlanes = P.t.planes, *__restrict__ qPlanes = P.q.planes;
+    for (int k = 0; k < nLong; k++) {
+        const uint4 d = lds128(sm + SM_SLOT + 16u * (uint32_t)(TILE - 1 - k));
+        const uint32_t v = (d.w >> 12) & 127u;
+        const bool mayN = anyN && (lds8(sm + SM_FLAG + v) & 16u) != 0u;
+        const int bases = (int)d.z;
+        int acc = 0;
+        for (int first = 0; first < bases; first += 1024 * LONG_STEPS) {         // LONG_STEPS steps of 1024 bases at a time
+            uint2 w[LONG_STEPS][4];
+#pragma unroll
+            for (int j = 0; j < LONG_STEPS; j++) {
+                const uint32_t word = (uint32_t)(first >> 5) + 32u * j + (uint32_t)lane;
+                w[j][0] = w[j][1] = w[j][2] = w[j][3] = make_uint2(0u, 0u);
+                if ((int)(word << 5) < bases) {
+                    w[j][0] = ldgPair(tPlanes + d.x + word); w[j][1] = ldgPair(tPlanes + d.x + word + 1);
+                    w[j][2] = ldgPair(qPlanes + d.y + word); w[j][3] = ldgPair(qPlanes + d.y + word + 1);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < LONG_STEPS; j++) {
+                if (first + 1024 * j < bases) {
+                    const uint32_t word = (uint32_t)(first >> 5) + 32u * j + (uint32_t)lane;
+                    const int left = bases - (int)(word << 5);
+                    uint32_t m = shrOnes(32u - (uint32_t)(left > 32 ? 32 : (left < 0 ? 0 : left)));
+                    if (mayN && left > 0) m &= nFreeMask(P.t.nplane, d.x + word, d.w & 31u, P.q.nplane, d.y + word, (d.w >> 5) & 31u);
+                    acc += scoreWindow<SYM>(P.coef, __funnelshift_r(w[j][0].x, w[j][1].x, d.w), __funnelshift_r(w[j][0].y, w[j][1].y, d.w),
+                                            __funnelshift_r(w[j][2].x, w[j][3].x, d.w >> 5), __funnelshift_r(w[j][2].y, w[j][3].y, d.w >> 5), m, __popc(m));
+                }
+            }
+        }
+        const int tot = __reduce_add_sync(FULL, acc);
+        if (lane == 0) { const uint32_t a = sm + SM_SCORE + 4u * v; sts(a, lds(a) + (uint32_t)tot); }
+    }
+}
+
+template <bool SYM, bool PLAIN, bool LONG>
 __global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
 scoreTilesKernel(const __grid_constant__ ScoreParams P)
 {
@@ -282,6 +334,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             bulkLoad(sm + SM_REC, P.blocks + tileBase, bytes, sm + SM_BAR);
         }
     }
+    if (LONG && lane == 0) sts(sm + SM_NLONG, 0u);
     constexpr int WORDS = CHUNK / 32;   // bitmap words per chunk; lane WORDS sees the next chunk's first word
     const uint32_t myHeadWord = __ldg(P.headBits + (size_t)chunk * WORDS + lane);
     const uint32_t j0 = __ldg(P.chunkJob + chunk);
@@ -349,8 +402,8 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
     // reads the records, validates them and issues every global load the sub-tile needs (first window of both genomes,
     // N summaries, gap cost); back() builds the item list and only then consumes the loads.  The halves of neighbouring
     // sub-tiles are interleaved (front 0, front 1, back 0, front 2, back 1, ...), so two sub-tiles' loads are in flight per
-    // warp and the shuffle chain of the list prefix runs under the memory latency.  The four sub-tiles are unrolled: every
-    // shared-memory offset is an immediate.
+    // warp and the shuffle chain of the list prefix runs under the memory latency.  The four sub-tiles are unrolled (every
+    // shared-memory offset an immediate) unless the instantiation streams long blocks (see streamLongBlocks).
     uint32_t seen = 0;                  // 1: some block of mine may contain N, 2: some block of mine is big (see back())
     int nSlots = 0;                     // blocks of this tile with more than 32 bases: they get a slot in the item list
     uint32_t itemBase = 0;              // items of the list so far
@@ -365,8 +418,8 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         // (the descriptor array has slack behind it: lanes without a block read whatever index they compute)
         uint4 infoN = ldgQuad(reinterpret_cast<const uint4 *>(P.info + jobC));
 
-        auto front = [&](auto subC) -> Front {
-            constexpr int sub = decltype(subC)::value;
+        auto front = [&](auto subC) -> Front {          // IntC<n> (unrolled) or int (loop)
+            const int sub = subC;
             Front F;
             const int v = sub * 32 + lane;
             const uint32_t hn = lds(sm + SM_HEAD + 4u * (uint32_t)(sub + 1));
@@ -425,11 +478,13 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         };
 
         auto back = [&](auto subC, const Front &F) {
-            constexpr int sub = decltype(subC)::value;
+            const int sub = subC;
             const int v = sub * 32 + lane;
             const uint32_t n = F.n;
-            // what is left of the block joins the warp's item list (nothing here waits for the loads)
-            const bool listed = n > 32u;
+            // what is left of the block joins the warp's item list (nothing here waits for the loads) -- unless the block is long:
+            // those are streamed after the rounds (streamLongBlocks), their descriptors fill the slot array from its far end
+            const bool isLong = LONG && n > LONG_BASES;
+            const bool listed = n > 32u && !isLong;
             const uint32_t cnt = listed ? (n - 1u) >> 5 : 0u;
             uint32_t inc = cnt;
 #pragma unroll
@@ -443,6 +498,16 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             }
             itemBase += __shfl_sync(FULL, inc, 31);
             nSlots += __popc(lb);
+            const uint32_t lbLong = LONG ? __ballot_sync(FULL, isLong) : 0u;
+            if (LONG && lbLong) {               // rare: the count lives in shared memory, not in a register of the hot path
+                const uint32_t have = lds(sm + SM_NLONG);
+                if (isLong)
+                    sts128(sm + SM_SLOT + 16u * ((uint32_t)(TILE - 1) - have - __popc(lbLong & (leMask >> 1))), F.tW + 1u, F.qW + 1u, n - 32u,
+                           (F.misc & 0x3ffu) | ((uint32_t)v << 12));
+                __syncwarp();
+                if (lane == 0) sts(sm + SM_NLONG, have + __popc(lbLong));
+                __syncwarp();
+            }
             // first 32 bases
             const uint32_t tSh = F.misc, qSh = F.misc >> 5;
             const uint32_t t1 = __funnelshift_r(F.ta.x, F.tb.x, tSh), t0 = __funnelshift_r(F.ta.y, F.tb.y, tSh);
@@ -463,10 +528,15 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             seen |= (mayN ? 1u : 0u) | ((n > P.smallBases) | ((uint32_t)(F.gap + (1 << 19)) >= (1u << 20)) ? 2u : 0u);
         };
 
-        { const Front F = front(IntC<0>()); back(IntC<0>(), F); }
-        { const Front F = front(IntC<1>()); back(IntC<1>(), F); }
-        { const Front F = front(IntC<2>()); back(IntC<2>(), F); }
-        { const Front F = front(IntC<3>()); back(IntC<3>(), F); }
+        if (LONG) {
+#pragma unroll 1
+            for (int sub = 0; sub < BPT; sub++) { const Front F = front(sub); back(sub, F); }
+        } else {
+            { const Front F = front(IntC<0>()); back(IntC<0>(), F); }
+            { const Front F = front(IntC<1>()); back(IntC<1>(), F); }
+            { const Front F = front(IntC<2>()); back(IntC<2>(), F); }
+            { const Front F = front(IntC<3>()); back(IntC<3>(), F); }
+        }
     }
     const bool anyN = __any_sync(FULL, (seen & 1u) != 0u), small = !__any_sync(FULL, (seen & 2u) != 0u);
     __syncwarp();
@@ -535,6 +605,10 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             const uint32_t a = sm + SM_SCORE + 4u * (lds(sm + SM_SLOT + 16u * (uint32_t)s + 12u) >> 12);
             sts(a, lds(a) + d);
         }
+    }
+    {
+        const uint32_t nLong = LONG ? lds(sm + SM_NLONG) : 0u;
+        if (nLong) streamLongBlocks<SYM>(P, sm, (int)nLong, lane, anyN);
     }
     __syncwarp();
 

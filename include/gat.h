@@ -110,6 +110,9 @@ typedef struct gat_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;
     uint32_t chunks;        /* CTAs of the scoring kernel */
+    uint32_t long_streamed; /* 1: the instantiation that streams blocks of more than 1056 bases ran (picked from a sample of
+                               the list's block sizes; both instantiations score every list exactly) */
+    uint32_t reserved;
 } gat_stats;
 
 const char *gat_last_error(void);

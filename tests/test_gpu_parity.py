@@ -13,6 +13,18 @@ import make_golden_helpers as helpers
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["auto", "stream", "list"])
+def long_blocks_mode(request, monkeypatch):
+    """Every test of this file runs three times: with the instantiation of the scoring kernel the library picks from the
+    list's block sizes, and with each of the two forced (the one that streams blocks of more than 1056 bases, the one
+    that lists every block).  Both must score every list exactly."""
+    if request.param != "auto":
+        monkeypatch.setenv("GAT_LONG_BLOCKS", request.param)
+    else:
+        monkeypatch.delenv("GAT_LONG_BLOCKS", raising=False)
+    return request.param
+
+
 def gpu_score(t, q, scoring, jobs, total, blocks):
     with ChainScorer(0) as sc:
         sc.load_genome("t", t)
@@ -208,6 +220,64 @@ def test_edge_cases(oracle, tmp_path):
     assert g[4] == 0 and g[5] == 0 and g[9] == 0      # all-N query, empty job
 
 
+@pytest.mark.parametrize("minus", [False, True])
+def test_long_block_lengths_around_the_streaming_threshold(oracle, golden, tmp_path, minus):
+    """Blocks of more than 1056 bases leave the item list and are streamed by the warp, 1024 bases a step and four steps a
+    group: lengths on both sides of each of those edges, with N runs inside some, next to short blocks in the same tile."""
+    rng = np.random.default_rng(11)
+    lens = [1055, 1056, 1057, 1058, 40, 1087, 1088, 1089, 7, 2079, 2080, 2081, 4127, 4128, 4129, 4130, 33, 5152, 5153, 8224, 8225,
+            12000, 1, 20001]
+    size = sum(lens) + 3 * len(lens) + 500
+    t_codes, q_codes = rng.integers(0, 4, size), rng.integers(0, 4, size + 77)
+    blocks, tp, qp = [], 11, 60
+    for n in lens:
+        q_codes[qp:qp + n] = np.where(rng.random(n) < 0.8, t_codes[tp:tp + n], q_codes[qp:qp + n])
+        blocks.append((tp, qp, n)); tp += n + 2; qp += n + 3
+    t = PackedGenome.from_codes(["t"], [t_codes], n_runs=np.array([(0, 2000, 30), (0, 9000, 1), (0, 30000, 2500)], dtype=NRUN_DTYPE))
+    if minus:                                                          # the chain runs on the query's minus strand
+        q_codes = (q_codes[::-1] ^ 2).copy()                          # T=0 C=1 A=2 G=3
+    q = PackedGenome.from_codes(["q"], [q_codes], n_runs=np.array([(0, 5000, 3), (0, 47000, 90)], dtype=NRUN_DTYPE))
+    blocks = np.array(blocks, dtype=BLOCK_DTYPE)
+    jobs = np.array([(0, QSEQ_MINUS if minus else 0, 0, 0, NO_CLIP_START, NO_CLIP_END),
+                     (0, QSEQ_MINUS if minus else 0, 0, len(lens), 1500, int(blocks["tStart"][-1]) + 5000)], dtype=JOB_DTYPE)
+    total = 2 * len(lens)
+    w = synth.Workload(t, q, jobs, total, blocks)
+    for matrix in (None, "synth_small/asym.q"):
+        m = os.path.join(golden, matrix) if matrix else None
+        g, l = gpu_score(t, q, scoring_of(golden, matrix, "loose"), jobs, total, blocks)
+        og, ol, _ = oracle_scores(oracle, w, ["t"], ["q"], m, "loose", tmp_path)
+        assert np.array_equal(g, og), (g, og)
+        assert np.array_equal(l, ol), (l, ol)
+    assert g[0] > 0
+
+
+def test_the_library_picks_the_instantiation_from_the_block_sizes(long_blocks_mode):
+    """gat_stats.long_streamed: short-block lists take the listing kernel, long-block lists the streaming one, for the
+    one-shot, the compact and the resident call alike; GAT_LONG_BLOCKS overrides."""
+    from genomealignmenttools_b200.records import pack_compact
+    names_t, names_q = ["chrA"], ["chrX"]
+    got = {}
+    for tag, kw in (("short", {}), ("long", dict(mean_log_len=7.5, sigma_log_len=0.8, max_len=16000))):
+        w = synth.make_workload(names_t, [4000000], names_q, [4000000], 6000, seed=21, telomere_n=100, **kw)
+        with ChainScorer(0) as sc:
+            sc.load_genome("t", w.t); sc.load_genome("q", w.q)
+            sc.set_scoring(Scoring(None, "loose"))
+            g0, l0 = sc.score(w.jobs, w.total, w.blocks)
+            a = sc.stats()["long_streamed"]
+            g1, l1 = sc.score_compact(*pack_compact(w.jobs, w.total, w.blocks))
+            b = sc.stats()["long_streamed"]
+            wl = sc.upload(w.jobs, w.total, w.blocks)
+            wl.run()
+            g2, l2 = wl.results()
+            c = sc.stats()["long_streamed"]
+            wl.free()
+        assert np.array_equal(g0, g1) and np.array_equal(g0, g2) and np.array_equal(l0, l1) and np.array_equal(l0, l2)
+        got[tag] = (a, b, c)
+    want = {"auto": {"short": (0, 0, 0), "long": (1, 1, 1)}, "stream": {"short": (1, 1, 1), "long": (1, 1, 1)},
+            "list": {"short": (0, 0, 0), "long": (0, 0, 0)}}[long_blocks_mode]
+    assert got == want
+
+
 def test_empty_and_invalid_worklists():
     w, _, _ = small_world(n_blocks=500)
     with ChainScorer(0) as sc:
@@ -290,6 +360,11 @@ def test_crossover_matches_oracle(oracle, tmp_path):
                 tsz, qsz = int(w.t.sizes[ti]), int(w.q.sizes[qi])
                 cases = crossover_cases(rng, tsz, qsz, 600)
                 cases += [(tsz, qsz, 0, 0, 64), (64, 64, tsz - 64, qsz - 64, 64), (1, 1, 0, 0, 1), (10, 10, 5, 5, 0)]
+                # long overlaps (beyond XOVER_SHORT the warp takes a pair, lane = base): word boundaries and several words
+                for ov in (65, 96, 97, 128, 500, 3000):
+                    for _ in range(6):
+                        lt, lq = int(rng.integers(ov, tsz)), int(rng.integers(ov, qsz))
+                        cases.append((lt, lq, int(rng.integers(0, tsz - ov)), int(rng.integers(0, qsz - ov)), ov))
                 # overlaps along planted homology: block starts of real chains, shifted against themselves
                 for j in np.nonzero((w.jobs["tSeq"] == ti) & ((w.jobs["qSeq"] & 0x7FFFFFFF) == qi) &
                                     ((w.jobs["qSeq"] >> 31) == (1 if strand == "-" else 0)))[0][:150]:

@@ -53,7 +53,7 @@ def test_libgatkent_exports_kents_entry_points():
 
 def test_record_layouts_match_header():
     assert BLOCK_DTYPE.itemsize == 12 and JOB_DTYPE.itemsize == 24 and NRUN_DTYPE.itemsize == 12
-    assert ctypes.sizeof(_native.GatStats) == 40
+    assert ctypes.sizeof(_native.GatStats) == 48
 
 
 def test_no_gpu_fails_loudly():
