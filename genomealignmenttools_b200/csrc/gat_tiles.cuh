@@ -250,17 +250,17 @@ __device__ __forceinline__ void warpJobReduce32(const ScoreParams &P, const uint
 }
 
 // LONG instantiations: blocks of more than LONG_BASES bases are not listed.  After the item rounds the warp streams them
-// one after the other, lane = word, 1024 bases per step and LONG_STEPS steps (8 loads per lane each) in flight; every lane
+// one after the other, lane = word, 1024 bases per step and LONG_STEPS steps (4 loads per lane each) in flight; every lane
 // keeps its own sum and one REDUX per block closes it: no owner search, no scan, no slot look-ups.  Descriptors (words of
 // the block's 33rd base, bases behind the first window, shifts and block index) sit at the far end of the slot array.
 //
 // Why a template parameter and not one kernel: the per-block path (phase 1 unrolled four times) is as large as the SM's
 // instruction cache takes -- with this loop behind it warps wait for instruction fetches (no_instruction 0.22 -> 1.84 per
 // issue, +17 % kernel time at 67-base blocks, profiles/README.md).  So the LONG instantiations run phase 1 as a loop (+3 %
-// at 67-base blocks) and stream long blocks (9-kb blocks: 0.42 -> 0.58 of the HBM roofline); the others list every block as
+// at 67-base blocks) and stream long blocks, four steps in flight (9-kb blocks: 0.42 -> 0.67 of the HBM roofline; two steps: 0.58); the others list every block as
 // before.  The host picks per work-list from a sample of the block sizes (gat_capi.cu: pickLong).
 constexpr uint32_t LONG_BASES = 32 + 1024;
-constexpr int LONG_STEPS = 2;           // steps (of 1024 bases) a warp keeps in flight per long block
+constexpr int LONG_STEPS = 4;           // steps (of 1024 bases) a warp keeps in flight per long block
 template <bool SYM>
 __device__ __forceinline__ void streamLongBlocks(const ScoreParams &P, uint32_t sm, int nLong, int lane, bool anyN)
 {

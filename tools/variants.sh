@@ -16,6 +16,6 @@ fi
 while [ $# -gt 1 ]; do
   tag=$1; flags=$2; shift 2
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Igenomealignmenttools_b200/csrc \
-     $flags -Xptxas -v --shared -o $OUT/libgat_$tag.so genomealignmenttools_b200/csrc/gat_capi.cu 2>&1 | grep -A2 "scoreTilesKernelILb1ELb1" | grep -E "registers|spill" | sed "s/^/$tag: /" &
+     $flags -Xptxas -v --shared -o $OUT/libgat_$tag.so genomealignmenttools_b200/csrc/gat_capi.cu 2>&1 | grep -A2 "scoreTilesKernelILb1ELb1ELb1" | grep -E "registers|spill" | sed "s/^/$tag: /" &
 done
 wait
