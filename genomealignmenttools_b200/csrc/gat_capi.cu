@@ -78,6 +78,7 @@ struct gat_ctx {
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
     uint32_t smallBases = 1;
+    bool pdl = true;                    // programmatic dependent launch of the pass's kernels (GAT_NO_PDL=1 turns it off)
     int forceLong = -1;                 // GAT_LONG_BLOCKS=stream / list in the environment at gat_create (tests, measurements): see pickLong
     std::vector<uint32_t> partJobs;    // gat_request_tuples(): jobs of the next scoring call whose tuple the caller wants
     gat_tuple *partOut = nullptr;
@@ -139,6 +140,7 @@ extern "C" int gat_create(gat_ctx **out, int device, void *stream)
         return fail(GAT_ECUDA, "gat_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
     gat_ctx *ctx = new gat_ctx();
     ctx->device = device;
+    if (const char *e = getenv("GAT_NO_PDL")) ctx->pdl = !(e[0] == '1');
     if (const char *e = getenv("GAT_LONG_BLOCKS")) {
         if (!strcmp(e, "stream")) ctx->forceLong = 1;
         else if (!strcmp(e, "list")) ctx->forceLong = 0;
@@ -420,6 +422,7 @@ static int shapeWorklist(gat_ctx *ctx, gat_worklist *wl, uint64_t nJobs, uint64_
         if (!wl->borrowedBlocks) CU(cudaMalloc(&wl->blocks, (cb + 3) * sizeof(gat_block)));   // slack: bulk copies round up to 16 bytes
         CU(cudaMalloc(&wl->chunkJob, (cc + 1) * sizeof(uint32_t)));
         CU(cudaMalloc(&wl->headBits, (headWords(cc) + 1) * sizeof(uint32_t)));     // + the mode word behind the bitmap
+        CU(cudaMemsetAsync(wl->headBits, 0, (headWords(cc) + 1) * sizeof(uint32_t), ctx->stream));
         CU(cudaMalloc(&wl->chunkHead, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTail, (cc + 1) * sizeof(Tup)));
         CU(cudaMalloc(&wl->chunkTailJob, (cc + 1) * sizeof(int)));
@@ -531,48 +534,65 @@ static int ensureTupleBuffer(gat_ctx *ctx, gat_worklist *wl)
 }
 
 // bitmap reset + jobPrepKernel: needs the jobs only, not the block records
+// The three kernels of a pass are launched with programmatic stream serialization (gat_kernels.cuh, dependsWait): each may
+// be scheduled while the kernel in front of it drains and waits on the device for it to complete.  GAT_NO_PDL=1 in the
+// environment at gat_create turns the attribute off (measurements).
+template <typename... KArgs, typename... Args>
+static cudaError_t launchDependent(gat_ctx *ctx, bool early, void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (ctx->pdl && early) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// (the job-start bitmap is all-zero here: zeroed when allocated, and fixupKernel clears what jobPrepKernel set)
 static int launchPrep(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 {
-    CU(cudaMemsetAsync(wl->headBits, 0, (headWords(wl->nChunks) + 1) * sizeof(uint32_t), st));
     const GenomeDev &t = ctx->genome[GAT_TARGET], &q = ctx->genome[GAT_QUERY];
     unsigned grid = (unsigned)((wl->nJobs + 1 + 255) / 256);
-    jobPrepKernel<<<grid, 256, 0, st>>>(wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
-                                        (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
-                                        wl->headBits, reinterpret_cast<int *>(wl->headBits + headWords(wl->nChunks)),
-                                        wl->outGlobal, wl->outLocal, ctx->err);
+    CU(launchDependent(ctx, true, jobPrepKernel, grid, 256, st, wl->jobs, wl->nJobs, wl->totalJobBlocks, (const int64_t *)t.seqBase, t.seqSize, t.nSeq,
+                       (const int64_t *)q.seqBase, q.seqSize, q.nSeq, wl->info, wl->chunkJob, wl->nChunks,
+                       wl->headBits, reinterpret_cast<int *>(wl->headBits + headWords(wl->nChunks)),
+                       wl->outGlobal, wl->outLocal, ctx->err));
     return GAT_OK;
 }
 
 // chunks [first, first + count)
 // `plain`: 1 / 0 = the list's mode as the host knows it, -1 = jobPrepKernel's verdict decides on the device: both
 // instantiations are launched and the one that does not apply returns at once.
+// `early`: the kernel in front of this launch in the stream is jobPrepKernel (the scoring kernel copies its records before
+// it waits for that kernel, so whatever wrote the records must have completed before jobPrepKernel did).
 template <bool PLAIN>
-static void launchTiles(gat_ctx *ctx, const ScoreParams &P, uint32_t count, bool streamLong, cudaStream_t st)
+static void launchTiles(gat_ctx *ctx, const ScoreParams &P, uint32_t count, bool streamLong, bool early, cudaStream_t st)
 {
     if (ctx->sym) {
-        if (streamLong) scoreTilesKernel<true, PLAIN, true><<<count, TPB, 0, st>>>(P);
-        else scoreTilesKernel<true, PLAIN, false><<<count, TPB, 0, st>>>(P);
+        if (streamLong) launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, true>, count, TPB, st, P);
+        else launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, false>, count, TPB, st, P);
     } else {
-        if (streamLong) scoreTilesKernel<false, PLAIN, true><<<count, TPB, 0, st>>>(P);
-        else scoreTilesKernel<false, PLAIN, false><<<count, TPB, 0, st>>>(P);
+        if (streamLong) launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, true>, count, TPB, st, P);
+        else launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, false>, count, TPB, st, P);
     }
 }
 
-static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, bool streamLong, cudaStream_t st)
+static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, bool streamLong, bool early, cudaStream_t st)
 {
     if (count == 0) return 0;
     P.chunkBase = first;
     int launches = 0;
-    if (plain != 0) { launchTiles<true>(ctx, P, count, streamLong, st); launches++; }
-    if (plain <= 0) { launchTiles<false>(ctx, P, count, streamLong, st); launches++; }
+    if (plain != 0) { launchTiles<true>(ctx, P, count, streamLong, early, st); launches++; }
+    if (plain <= 0) { launchTiles<false>(ctx, P, count, streamLong, early, st); launches++; }
     return launches;
 }
 
 static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 {
-    fixupKernel<<<(wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, 0, st>>>(wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead, wl->chunkTail,
-                                                                           wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal,
-                                                                           ctx->partJobs.empty() ? nullptr : wl->outTuple, ctx->err);
+    launchDependent(ctx, true, fixupKernel, (wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, st, wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead,
+                    wl->chunkTail, wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->partJobs.empty() ? nullptr : wl->outTuple,
+                    ctx->err, wl->headBits, (uint32_t)(headWords(wl->nChunks) + 1));
 }
 
 extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
@@ -599,7 +619,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     rc = launchPrep(ctx, wl, st);
     if (rc != GAT_OK) return rc;
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, st);
+    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, true, st);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     launchFixup(ctx, wl, st);
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
@@ -803,7 +823,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
             rc = launchPrep(ctx, wl, st);
             if (rc != GAT_OK) return rc;
             if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, st);
+            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, true, st);
             if (prof) CU(cudaEventRecord(ctx->ev[2], st));
         } else {
             rc = launchPrep(ctx, wl, st);
@@ -819,7 +839,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                 CU(cudaStreamWaitEvent(st, ctx->sliceEv[s], 0));
                 expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
-                launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, st);
+                launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, false, st);      // (behind expandBlocksKernel: no early start)
                 sliceLaunches += 2;
             }
             ctx->stats.kernel_launches = sliceLaunches - 2;

@@ -312,6 +312,16 @@ __device__ __forceinline__ gat_block loadBlock(const gat_block *__restrict__ blo
     return r;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The kernels of one scoring pass (jobPrepKernel -> scoreTilesKernel -> fixupKernel) are launched with programmatic
+// stream serialization: a kernel's CTAs may be scheduled while the kernel in front of it in the stream drains, and
+// dependsWait() is where it stops until that kernel has completed and its writes are visible.  Whatever a kernel does
+// before dependsWait() must not touch anything the kernel in front of it (or any kernel that one waits for) writes.
+// In a kernel launched without the attribute both are no-ops.
+__device__ __forceinline__ void dependsWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void dependentsMayLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+
 // ------------------------------------------------------------------ job preparation
 // One thread per job: gat_job -> JobInfo (sequence bases and sizes resolved once per job instead of once
 // per block), zero scores for empty jobs (kent: NULL sub-chain), CSR validation, and chunkJob[c] = the job
@@ -324,6 +334,8 @@ __global__ void jobPrepKernel(const gat_job *__restrict__ jobs, unsigned long lo
                               long long *__restrict__ outGlobal, long long *__restrict__ outLocal, int *__restrict__ err)
 {
     const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    dependsWait();                  // (the fix-up kernel of the pass before this one reads what this kernel writes)
+    dependentsMayLaunch();          // the scoring kernel starts on its record copies meanwhile
     JobInfo o;
     o.tBaseW = o.qBaseW = o.tSize = o.qSize = 0; o.clipStart = o.clipEnd = 0; o.delta = 0;
     o.blockPtr = (uint32_t)total;                       // sentinel record nJobs closes the CSR
@@ -514,7 +526,8 @@ __global__ void __launch_bounds__(FIX_TPB)
 fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned long long total,
             const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
             const int *__restrict__ chunkTailJob, uint32_t nChunks,
-            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, Tup *__restrict__ outTuple, const int *__restrict__ err)
+            long long *__restrict__ outGlobal, long long *__restrict__ outLocal, Tup *__restrict__ outTuple, const int *__restrict__ err,
+            uint32_t *__restrict__ headBits, uint32_t headBitsWords)
 {
     __shared__ uint32_t sLongC[FIX_TPB], sLongN[FIX_TPB];
     __shared__ int sLongJ[FIX_TPB];
@@ -522,6 +535,16 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
     __shared__ Tup sPart[FIX_TPB / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x * FIX_TPB + tid;
+    dependsWait();
+    dependentsMayLaunch();
+    // the job-start bitmap goes back to all-zero for the next pass (jobPrepKernel sets bits with atomicOr; the words
+    // behind the last chunk hold the closing bit, the slack and the mode word)
+    if (c < nChunks) {
+        uint4 *w = reinterpret_cast<uint4 *>(headBits + (size_t)c * (CHUNK / 32));
+        w[0] = make_uint4(0u, 0u, 0u, 0u); w[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (c + 1 == nChunks)
+            for (size_t k = (size_t)nChunks * (CHUNK / 32); k < headBitsWords; k++) headBits[k] = 0u;
+    }
     if (*err) return;
     if (tid == 0) sNLong = 0;
     __syncthreads();

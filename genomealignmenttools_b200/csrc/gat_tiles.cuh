@@ -335,6 +335,10 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         }
     }
     if (LONG && lane == 0) sts(sm + SM_NLONG, 0u);
+    // (up to here nothing was read that jobPrepKernel writes: the records are the caller's, or expandBlocksKernel's, which
+    //  jobPrepKernel waited for)
+    dependsWait();
+    dependentsMayLaunch();
     constexpr int WORDS = CHUNK / 32;   // bitmap words per chunk; lane WORDS sees the next chunk's first word
     const uint32_t myHeadWord = __ldg(P.headBits + (size_t)chunk * WORDS + lane);
     const uint32_t j0 = __ldg(P.chunkJob + chunk);
