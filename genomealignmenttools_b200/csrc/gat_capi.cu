@@ -96,6 +96,7 @@ struct gat_worklist {
     bool borrowedBlocks = false;        // blocks belong to another work-list (re-run without empty jobs)
     int plain = -1;                     // 1: whole chains tiling the record array (PLAIN kernel), 0: clips / shared records,
                                         // -1: not known on the host, jobPrepKernel decides (both instantiations are launched)
+    bool searchJobs = false;            // the list has empty jobs: SEARCH instantiation (job of a block looked up in the CSR, gat_kernels.cuh)
     bool streamLong = true;             // LONG instantiation (blocks of more than 1056 bases are streamed, gat_tiles.cuh): pickLong()
     Tup *chunkHead = nullptr, *chunkTail = nullptr;
     int *chunkTailJob = nullptr;
@@ -391,7 +392,7 @@ extern "C" int gat_set_scoring(gat_ctx *ctx, const gat_scoring *s)
     ctx->dynSmem = 0;       // the small gap tables are read through L1
     {
         int perSm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, scoreTilesKernel<true, true, false>, TPB, ctx->dynSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, scoreTilesKernel<true, true, false, false>, TPB, ctx->dynSmem));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         ctx->residentCtas = (uint32_t)(perSm > 0 ? perSm : 1) * (uint32_t)sms;
     }
@@ -486,8 +487,10 @@ extern "C" int gat_worklist_create(gat_ctx *ctx, const gat_job *jobs, uint64_t n
     int rc = allocWorklist(ctx, nJobs, totalJobBlocks, nBlocks, &wl);
     if (rc == GAT_OK) {     // a resident list is looked at once: whole chains tiling the record array take the PLAIN kernel
         wl->plain = totalJobBlocks <= nBlocks ? 1 : 0;
-        for (uint64_t j = 0; j < nJobs && wl->plain; j++)
+        for (uint64_t j = 0; j < nJobs; j++) {
             if (jobs[j].firstBlock != jobs[j].blockPtr || jobs[j].clipStart != GAT_NO_CLIP_START || jobs[j].clipEnd != GAT_NO_CLIP_END) wl->plain = 0;
+            if ((j + 1 < nJobs ? jobs[j + 1].blockPtr : totalJobBlocks) <= jobs[j].blockPtr) wl->searchJobs = true;      // an empty job
+        }
     }
     if (rc == GAT_OK) wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, 0x7fffffffu);
     if (rc == GAT_OK) rc = uploadWorklist(ctx, wl, jobs, blocks);
@@ -567,24 +570,27 @@ static int launchPrep(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 // `early`: the kernel in front of this launch in the stream is jobPrepKernel (the scoring kernel copies its records before
 // it waits for that kernel, so whatever wrote the records must have completed before jobPrepKernel did).
 template <bool PLAIN>
-static void launchTiles(gat_ctx *ctx, const ScoreParams &P, uint32_t count, bool streamLong, bool early, cudaStream_t st)
+static void launchTiles(gat_ctx *ctx, const ScoreParams &P, uint32_t count, bool streamLong, bool searchJobs, bool early, cudaStream_t st)
 {
-    if (ctx->sym) {
-        if (streamLong) launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, true>, count, TPB, st, P);
-        else launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, false>, count, TPB, st, P);
+    if (searchJobs) {           // lists with empty jobs (rare): one instantiation per matrix kind
+        if (ctx->sym) launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, true, true>, count, TPB, st, P);
+        else launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, true, true>, count, TPB, st, P);
+    } else if (ctx->sym) {
+        if (streamLong) launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, true, false>, count, TPB, st, P);
+        else launchDependent(ctx, early, scoreTilesKernel<true, PLAIN, false, false>, count, TPB, st, P);
     } else {
-        if (streamLong) launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, true>, count, TPB, st, P);
-        else launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, false>, count, TPB, st, P);
+        if (streamLong) launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, true, false>, count, TPB, st, P);
+        else launchDependent(ctx, early, scoreTilesKernel<false, PLAIN, false, false>, count, TPB, st, P);
     }
 }
 
-static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, bool streamLong, bool early, cudaStream_t st)
+static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t count, int plain, bool streamLong, bool searchJobs, bool early, cudaStream_t st)
 {
     if (count == 0) return 0;
     P.chunkBase = first;
     int launches = 0;
-    if (plain != 0) { launchTiles<true>(ctx, P, count, streamLong, early, st); launches++; }
-    if (plain <= 0) { launchTiles<false>(ctx, P, count, streamLong, early, st); launches++; }
+    if (plain != 0) { launchTiles<true>(ctx, P, count, streamLong, searchJobs, early, st); launches++; }
+    if (plain <= 0) { launchTiles<false>(ctx, P, count, streamLong, searchJobs, early, st); launches++; }
     return launches;
 }
 
@@ -592,7 +598,7 @@ static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
 {
     launchDependent(ctx, true, fixupKernel, (wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, st, wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead,
                     wl->chunkTail, wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->partJobs.empty() ? nullptr : wl->outTuple,
-                    ctx->err, wl->headBits, (uint32_t)(headWords(wl->nChunks) + 1));
+                    ctx->err, wl->headBits, (uint32_t)(headWords(wl->nChunks) + 1), wl->searchJobs ? ~ERR_EMPTYJOB : ~0);
 }
 
 extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
@@ -619,7 +625,7 @@ extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
     rc = launchPrep(ctx, wl, st);
     if (rc != GAT_OK) return rc;
     if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, true, st);
+    const int scoreLaunches = launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, wl->searchJobs, true, st);
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     launchFixup(ctx, wl, st);
     if (prof) CU(cudaEventRecord(ctx->ev[3], st));
@@ -657,73 +663,44 @@ static int rejectWorklist(int err)
                 (err & ERR_CSR) ? " blockPtr is not a non-decreasing CSR row pointer starting at 0;" : "");
 }
 
-// The scoring kernel numbers jobs by counting job starts, which presumes that every job owns at least one
-// job-block.  Work-lists with empty jobs (a sub-chain that clips to nothing: kent's NULL sub-chain, score 0)
-// are rare; jobPrepKernel flags them and the list is scored again here without them.
-static int rerunWithoutEmptyJobs(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local)
-{
-    std::vector<gat_job> all(wl->nJobs), kept;
-    std::vector<uint64_t> origin;
-    CU(cudaMemcpyAsync(all.data(), wl->jobs, wl->nJobs * sizeof(gat_job), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (uint64_t j = 0; j < wl->nJobs; j++) {
-        const uint64_t np = j + 1 < wl->nJobs ? all[j + 1].blockPtr : wl->totalJobBlocks;
-        if (np > all[j].blockPtr) { kept.push_back(all[j]); origin.push_back(j); }
-    }
-    gat_worklist tmp;
-    tmp.borrowedBlocks = true;
-    tmp.plain = -1;
-    tmp.streamLong = wl->streamLong;
-    int rc = shapeWorklist(ctx, &tmp, kept.size(), wl->totalJobBlocks, wl->nBlocks);
-    tmp.blocks = wl->blocks;
-    std::vector<int64_t> g(kept.size()), l(kept.size());
-    if (rc == GAT_OK && !kept.empty()) {
-        cudaError_t e = cudaMemcpyAsync(tmp.jobs, kept.data(), kept.size() * sizeof(gat_job), cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = fail(GAT_ECUDA, "work-list upload failed: %s", cudaGetErrorString(e));
-        if (rc == GAT_OK) rc = gat_worklist_run(ctx, &tmp);
-        if (rc == GAT_OK) {
-            cudaMemcpyAsync(g.data(), tmp.outGlobal, g.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
-            cudaMemcpyAsync(l.data(), tmp.outLocal, l.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
-            int err = 0;
-            rc = readDeviceError(ctx, &err);
-            if (rc == GAT_OK && err) rc = rejectWorklist(err);
-        }
-    }
-    cudaStreamSynchronize(ctx->stream);
-    tmp.blocks = nullptr;
-    freeWorklistBuffers(&tmp);
-    if (rc != GAT_OK) return rc;
-    for (uint64_t j = 0; j < wl->nJobs; j++) { if (global) global[j] = 0; if (local) local[j] = 0; }
-    for (size_t k = 0; k < kept.size(); k++) { if (global) global[origin[k]] = g[k]; if (local) local[origin[k]] = l[k]; }
-    return GAT_OK;
-}
-
+// The scoring kernel numbers jobs by counting job starts, which presumes that every job owns at least one job-block.
+// Work-lists with empty jobs (a sub-chain that clips to nothing: kent's NULL sub-chain, score 0) take the SEARCH
+// instantiation, which looks the job of a block up in the CSR.  gat_worklist_create sees them on the host; for a
+// one-shot list jobPrepKernel reports them (ERR_EMPTYJOB: the ordinary kernel leaves at once), and the list, still on
+// the device, is scored again here with the SEARCH instantiation: no copy back, no host filter, no buffers.
 extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local)
 {
     if (!ctx || !wl) return fail(GAT_EINVAL, "gat_worklist_results: NULL argument");
     CU(cudaSetDevice(ctx->device));
-    if (wl->nJobs) {
-        if (global) CU(cudaMemcpyAsync(global, wl->outGlobal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-        if (local) CU(cudaMemcpyAsync(local, wl->outLocal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int pass = 0; pass < 2; pass++) {
+        if (wl->nJobs) {
+            if (global) CU(cudaMemcpyAsync(global, wl->outGlobal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            if (local) CU(cudaMemcpyAsync(local, wl->outLocal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        const std::vector<uint32_t> &parts = ctx->partJobs;          // a request covers one scoring call
+        if (!parts.empty()) {
+            if (!wl->outTuple || wl->capTuples < wl->nJobs) { ctx->partJobs.clear(); return fail(GAT_ESTATE, "gat_request_tuples must precede the scoring call"); }
+            for (size_t k = 0; k < parts.size(); k++)
+                CU(cudaMemcpyAsync(ctx->partOut + k, wl->outTuple + parts[k], sizeof(gat_tuple), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        int err = 0;
+        int rc = readDeviceError(ctx, &err);
+        if (rc != GAT_OK) { ctx->partJobs.clear(); return rc; }
+        if (wl->searchJobs) err &= ~ERR_EMPTYJOB;
+        if (err & ~ERR_EMPTYJOB) { ctx->partJobs.clear(); return rejectWorklist(err); }
+        if (err & ERR_EMPTYJOB) {           // first sight of an empty job in this list: once more, looking jobs up
+            wl->searchJobs = true;
+            rc = gat_worklist_run(ctx, wl);
+            if (rc != GAT_OK) { ctx->partJobs.clear(); return rc; }
+            continue;
+        }
+        break;
     }
     std::vector<uint32_t> parts;
-    parts.swap(ctx->partJobs);          // a request covers one scoring call
-    if (!parts.empty()) {
-        if (!wl->outTuple || wl->capTuples < wl->nJobs) return fail(GAT_ESTATE, "gat_request_tuples must precede the scoring call");
-        for (size_t k = 0; k < parts.size(); k++)
-            CU(cudaMemcpyAsync(ctx->partOut + k, wl->outTuple + parts[k], sizeof(gat_tuple), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    int err = 0;
-    int rc = readDeviceError(ctx, &err);
-    if (rc != GAT_OK) return rc;
-    if (err & ~ERR_EMPTYJOB) return rejectWorklist(err);
+    parts.swap(ctx->partJobs);
     for (size_t k = 0; k < parts.size(); k++)       // still the fill pattern: the job was not finished by the fix-up kernel
         if ((uint64_t)ctx->partOut[k].c == 0x8080808080808080ull)
             return fail(GAT_EINVAL, "gat_request_tuples: job %u owns fewer than GAT_TUPLE_MIN_BLOCKS job-blocks", parts[k]);
-    if (err & ERR_EMPTYJOB) {
-        rc = rerunWithoutEmptyJobs(ctx, wl, global, local);
-        if (rc != GAT_OK) return rc;
-    }
     return finishStats(ctx);
 }
 
@@ -740,6 +717,7 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
     gat_worklist *wl = ctx->scratch;
     int rc = shapeWorklist(ctx, wl, nJobs, totalJobBlocks, nBlocks);
     wl->plain = -1;
+    wl->searchJobs = false;
     wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, 0x7fffffffu);
     cudaStream_t st = ctx->stream;
     const bool prof = ctx->profiling;
@@ -773,6 +751,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     int rc = shapeWorklist(ctx, wl, nJobs, nBlocks, nBlocks);
     if (rc != GAT_OK) return rc;
     wl->plain = 1;              // whole chains by construction
+    wl->searchJobs = false;
     wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, GAT_CBLOCK_MAX_SIZE);
     cudaStream_t st = ctx->stream;
     const uint64_t nGroups = (nBlocks + GAT_CGROUP - 1) / GAT_CGROUP;
@@ -823,7 +802,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
             rc = launchPrep(ctx, wl, st);
             if (rc != GAT_OK) return rc;
             if (prof) CU(cudaEventRecord(ctx->ev[1], st));
-            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, true, st);
+            launchScoring(ctx, P, 0, wl->nChunks, wl->plain, wl->streamLong, wl->searchJobs, true, st);
             if (prof) CU(cudaEventRecord(ctx->ev[2], st));
         } else {
             rc = launchPrep(ctx, wl, st);
@@ -839,7 +818,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                 CU(cudaStreamWaitEvent(st, ctx->sliceEv[s], 0));
                 expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
-                launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, false, st);      // (behind expandBlocksKernel: no early start)
+                launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, wl->searchJobs, false, st);      // (behind expandBlocksKernel: no early start)
                 sliceLaunches += 2;
             }
             ctx->stats.kernel_launches = sliceLaunches - 2;

@@ -404,6 +404,25 @@ __device__ __forceinline__ JobInfo loadInfo(const JobInfo *__restrict__ info, ui
     return r;
 }
 
+// SEARCH instantiations (work-lists with empty jobs: kent's NULL sub-chains, chain.c:535-539): the job of job-block v is
+// looked up in the CSR -- the last job whose blockPtr is <= v, which is the one that owns v because the empty jobs in
+// front of it share its blockPtr -- instead of counted from the job-start bitmap, which presumes that consecutive job
+// starts belong to consecutive jobs.  info[nJobs] is the sentinel (blockPtr = total).
+__device__ __noinline__ uint32_t searchJob(const JobInfo *__restrict__ info, unsigned long long nJobs, uint32_t v)
+{
+    uint32_t lo = 0, hi = (uint32_t)nJobs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&info[mid].blockPtr) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+template <bool SEARCH>
+__device__ __forceinline__ uint32_t jobOf(const ScoreParams &P, uint32_t counted, uint32_t v)
+{
+    return SEARCH ? searchJob(P.info, P.nJobs, v) : counted;
+}
+
 template <typename T> __device__ __forceinline__ long long finalLocal(const TupT<T> &t)
 {   // a job's running score ends at max(c, d) (entered with 0) and its last peak test is still due
     return max64(0, max64(max64(widen(t.c), (long long)t.d), max64(widen(t.e), widen(t.f))));
@@ -412,9 +431,9 @@ __device__ __forceinline__ long long finalLocal(const Tup &t) { return max64(0, 
 
 // Phase 3 of scoreChunksKernel for one warp (see there), in 32- or 64-bit tuples.  Lane l holds job-blocks
 // 4l..4l+3 of the warp: scores a[], gap costs g[] (the gap BEFORE the block), flags fl4 (one byte each).
-template <typename T>
+template <typename T, bool SEARCH>
 __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
-                                              uint32_t myWr, uint32_t myHw, int warpV0, int vEnd,
+                                              uint32_t myWr, uint32_t myHw, uint32_t vb0, int warpV0, int vEnd,
                                               int warp, int lane, Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead,
                                               int *sWarpPendJob, int *sLastIsEnd, uint32_t *sLastJob)
 {
@@ -442,14 +461,14 @@ __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&
             }
             const int v = warpV0 + BPT * lane + k;
             if (fl & 2) {
-                const uint32_t job = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31))));
+                const uint32_t job = jobOf<SEARCH>(P, myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31)))), vb0 + (uint32_t)v);
                 if (runHasHead) {   // job lies inside my run: done
                     P.outGlobal[job] = (long long)cur.d;
                     P.outLocal[job] = finalLocal(cur);
                 } else { pend = true; pendTup = cur; pendJob = job; }
                 if (v + 1 == vEnd) { *sLastIsEnd = 1; *sLastJob = job; }
             } else if (v + 1 == vEnd) {          // the chunk's last valid job-block: its job runs on
-                *sLastIsEnd = 0; *sLastJob = myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31))));
+                *sLastIsEnd = 0; *sLastJob = jobOf<SEARCH>(P, myWr + __popc(myHw & (0xffffffffu >> (31 - (v & 31)))), vb0 + (uint32_t)v);
             }
         }
     }
@@ -481,13 +500,14 @@ __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&
 }
 
 // the 64-bit form is rare (a warp whose 128 blocks sum past 2^27): keep it out of the hot instruction stream
+template <bool SEARCH>
 __device__ __noinline__ void warpJobReduceWide(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,
-                                               uint32_t myWr, uint32_t myHw, int warpV0, int vEnd,
+                                               uint32_t myWr, uint32_t myHw, uint32_t vb0, int warpV0, int vEnd,
                                                int warp, int lane, Tup *sWarpAgg, Tup *sWarpPend, int *sWarpHead,
                                                int *sWarpPendJob, int *sLastIsEnd, uint32_t *sLastJob)
 {
-    warpJobReduce<long long>(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane, sWarpAgg, sWarpPend, sWarpHead,
-                             sWarpPendJob, sLastIsEnd, sLastJob);
+    warpJobReduce<long long, SEARCH>(P, a, g, fl4, myWr, myHw, vb0, warpV0, vEnd, warp, lane, sWarpAgg, sWarpPend, sWarpHead,
+                                     sWarpPendJob, sLastIsEnd, sLastJob);
 }
 
 // ------------------------------------------------------------------ cross-chunk fix-up
@@ -527,7 +547,7 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
             const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
             const int *__restrict__ chunkTailJob, uint32_t nChunks,
             long long *__restrict__ outGlobal, long long *__restrict__ outLocal, Tup *__restrict__ outTuple, const int *__restrict__ err,
-            uint32_t *__restrict__ headBits, uint32_t headBitsWords)
+            uint32_t *__restrict__ headBits, uint32_t headBitsWords, int fatal)
 {
     __shared__ uint32_t sLongC[FIX_TPB], sLongN[FIX_TPB];
     __shared__ int sLongJ[FIX_TPB];
@@ -545,7 +565,7 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
         if (c + 1 == nChunks)
             for (size_t k = (size_t)nChunks * (CHUNK / 32); k < headBitsWords; k++) headBits[k] = 0u;
     }
-    if (*err) return;
+    if (*err & fatal) return;       // (lists with empty jobs scored by the SEARCH instantiation: ERR_EMPTYJOB is not an error)
     if (tid == 0) sNLong = 0;
     __syncthreads();
     int j = -1;

@@ -181,8 +181,9 @@ __device__ __noinline__ int gapCostBeyond(const ScoreParams &P, int dq, int dt)
 // block has flags 0, score 0, gap 0 and passes through as a continuation).  Job scores are the max-plus tuples of Tup
 // (gat_kernels.cuh), reduced in order: four blocks per lane, then one segmented warp scan in which "the nearest lane at
 // or below me whose blocks contain a job start" comes from a ballot, so only the four tuple words are shuffled.
+template <bool SEARCH>
 __device__ __forceinline__ void warpJobReduce32(const ScoreParams &P, const uint4 a4, const uint4 g4, const uint32_t fl4,
-                                                const uint32_t myWr, const uint32_t myHw, const int lane, const uint32_t leMask,
+                                                const uint32_t myWr, const uint32_t myHw, const uint32_t tileBase, const int lane, const uint32_t leMask,
                                                 const int lastIdx, Tup *warpAgg, Tup *warpPend, int *warpHead, int *warpPendJob,
                                                 int *sLastIsEnd, uint32_t *sLastJob)
 {
@@ -208,16 +209,17 @@ __device__ __forceinline__ void warpJobReduce32(const ScoreParams &P, const uint
         c = plain && !head ? tc : c + av;
         d += dY;
         if (end) {
+            const uint32_t jb = jobOf<SEARCH>(P, job, tileBase + 4u * (uint32_t)lane + (uint32_t)k);
             if (seenHead) {             // the job lies inside my blocks: done
-                P.outGlobal[job] = (long long)d;
-                P.outLocal[job] = (long long)max(max(0, max(c, d)), max(e, f));
-            } else { pend = true; pd = d; pc = c; pe = e; pf = f; pendJob = job; }
+                P.outGlobal[jb] = (long long)d;
+                P.outLocal[jb] = (long long)max(max(0, max(c, d)), max(e, f));
+            } else { pend = true; pd = d; pc = c; pe = e; pf = f; pendJob = jb; }
         }
     }
     // the chunk's last job-block: does its job run on into the next chunk?  (the fix-up kernel wants to know)
     if ((lastIdx >> 2) == lane && lastIdx >= 0) {
         *sLastIsEnd = ((fl4 >> (8 * (lastIdx & 3))) & 2u) != 0;
-        *sLastJob = myWr + __popc(myHw & (0xffffffffu >> (31 - (lastIdx & 31))));
+        *sLastJob = jobOf<SEARCH>(P, myWr + __popc(myHw & (0xffffffffu >> (31 - (lastIdx & 31)))), tileBase + (uint32_t)lastIdx);
     }
     // segmented inclusive scan over the lanes: lane i takes in lanes down to the nearest one whose blocks contain a job start
     const uint32_t headMask = __ballot_sync(FULL, seenHead);
@@ -299,7 +301,7 @@ __device__ __forceinline__ void streamLongBlocks(const ScoreParams &P, uint32_t 
     }
 }
 
-template <bool SYM, bool PLAIN, bool LONG>
+template <bool SYM, bool PLAIN, bool LONG, bool SEARCH>
 __global__ void __launch_bounds__(TPB, GAT_MIN_CTAS)
 scoreTilesKernel(const __grid_constant__ ScoreParams P)
 {
@@ -350,7 +352,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
     }
     // rejected by jobPrepKernel (or an empty job), or the other instantiation's list: leave (as a whole warp, and never
     // while a copy into this CTA's shared memory is in flight)
-    if (__any_sync(FULL, verdict != 0 || ((mode & MODE_GENERAL) != 0) == PLAIN)) {
+    if (__any_sync(FULL, (SEARCH ? verdict & ~ERR_EMPTYJOB : verdict) != 0 || ((mode & MODE_GENERAL) != 0) == PLAIN)) {
         if (PLAIN && nLive > 0) mbarWait(sm + SM_BAR, 0);
         return;
     }
@@ -379,7 +381,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
 #pragma unroll 1
         for (int sub = 0; sub < BPT; sub++) {
             const uint32_t hw = lds(sm + SM_HEAD + 4u * (uint32_t)sub);
-            const uint32_t job = lds(sm + SM_RANK + 4u * (uint32_t)sub) + __popc(hw & leMask);
+            const uint32_t job = jobOf<SEARCH>(P, lds(sm + SM_RANK + 4u * (uint32_t)sub) + __popc(hw & leMask), tileBase + 32u * (uint32_t)sub + (uint32_t)lane);
             const bool isHead = ((hw >> lane) & 1u) != 0;
             const int v = sub * 32 + lane;
             const bool valid = v < nValid;
@@ -418,7 +420,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         const uint32_t flagA = sm + SM_FLAG + (uint32_t)lane;
         const uint32_t D = (uint32_t)P.gap.denseSize;
         uint32_t hwC = lds(sm + SM_HEAD);
-        uint32_t jobC = lds(sm + SM_RANK) + __popc(hwC & leMask);
+        uint32_t jobC = jobOf<SEARCH>(P, lds(sm + SM_RANK) + __popc(hwC & leMask), tileBase + (uint32_t)lane);
         // (the descriptor array has slack behind it: lanes without a block read whatever index they compute)
         uint4 infoN = ldgQuad(reinterpret_cast<const uint4 *>(P.info + jobC));
 
@@ -437,7 +439,7 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
             }
             hwC = hn;
             if (sub + 1 < BPT) {                        // the next sub-tile's job descriptor is fetched a sub-tile ahead
-                jobC = lds(sm + SM_RANK + 4u * (uint32_t)(sub + 1)) + __popc(hn & leMask);
+                jobC = jobOf<SEARCH>(P, lds(sm + SM_RANK + 4u * (uint32_t)(sub + 1)) + __popc(hn & leMask), tileBase + 32u * (uint32_t)(sub + 1) + (uint32_t)lane);
                 infoN = ldgQuad(reinterpret_cast<const uint4 *>(P.info + jobC));
             }
             // my record and the one in front of it
@@ -625,12 +627,12 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
         // bitmap word of my four blocks and the job rank in front of it (job = rank + popc(word & lanes up to the block))
         const uint32_t myWr = lds(sm + SM_RANK + 4u * (uint32_t)(lane >> 3)), myHw = lds(sm + SM_HEAD + 4u * (uint32_t)(lane >> 3));
         if (small) {
-            warpJobReduce32(P, a4, g4, fl4, myWr, myHw, lane, leMask, vEnd - 1 - warpV0,
+            warpJobReduce32<SEARCH>(P, a4, g4, fl4, myWr, myHw, tileBase, lane, leMask, vEnd - 1 - warpV0,
                             &sWarpAgg[warp], &sWarpPend[warp], &sWarpHead[warp], &sWarpPendJob[warp], &sLastIsEnd, &sLastJob);
         } else {
             const int a[BPT] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
             const int g[BPT] = {(int)g4.x, (int)g4.y, (int)g4.z, (int)g4.w};
-            warpJobReduceWide(P, a, g, fl4, myWr, myHw, warpV0, vEnd, warp, lane,
+            warpJobReduceWide<SEARCH>(P, a, g, fl4, myWr, myHw, vb0, warpV0, vEnd, warp, lane,
                               sWarpAgg, sWarpPend, sWarpHead, sWarpPendJob, &sLastIsEnd, &sLastJob);
         }
     }

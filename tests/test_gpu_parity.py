@@ -278,6 +278,41 @@ def test_the_library_picks_the_instantiation_from_the_block_sizes(long_blocks_mo
     assert got == want
 
 
+@pytest.mark.parametrize("clip", [False, True])
+def test_empty_jobs_anywhere_in_the_list(clip):
+    """kent's NULL sub-chains (chain.c:535-539) as jobs without job-blocks: in front, at the end, in runs, on chunk
+    boundaries.  They score 0 and every other job scores what it scores in the list without them -- through the one-shot
+    call (the device reports them and the list is scored again where it lies), the resident list (seen on the host) and a
+    second one-shot call on the same context (the scratch list forgets)."""
+    w, _, _ = small_world(seed=5, n_blocks=40000, max_chain_blocks=3000)
+    jobs = w.jobs.copy()
+    if clip:                                            # clipped jobs take the general kernel
+        jobs["clipStart"][::3] = 0
+    rng = np.random.default_rng(8)
+    n = len(jobs)
+    where = np.sort(np.concatenate([[0, 0, 0, n, n], rng.integers(0, n + 1, 300), np.repeat(rng.integers(0, n + 1, 10), 7)]))
+    ptr_of = np.append(jobs["blockPtr"], w.total)
+    empties = np.zeros(len(where), dtype=JOB_DTYPE)
+    empties["blockPtr"] = ptr_of[where]; empties["firstBlock"] = empties["blockPtr"]
+    empties["tSeq"] = 0; empties["qSeq"] = 0; empties["clipStart"] = NO_CLIP_START; empties["clipEnd"] = NO_CLIP_END
+    mixed = np.insert(jobs, where, empties)
+    is_empty = np.insert(np.zeros(n, dtype=bool), where, True)
+    assert np.all(np.diff(mixed["blockPtr"].astype(np.int64)) >= 0)
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(Scoring(None, "medium"))
+        g0, l0 = sc.score(jobs, w.total, w.blocks)
+        g1, l1 = sc.score(mixed, w.total, w.blocks)
+        wl = sc.upload(mixed, w.total, w.blocks)
+        wl.run(); g2, l2 = wl.results()
+        wl.run(); g3, l3 = wl.results()
+        wl.free()
+        g4, l4 = sc.score(jobs, w.total, w.blocks)
+    for g, l in ((g1, l1), (g2, l2), (g3, l3)):
+        assert np.all(g[is_empty] == 0) and np.all(l[is_empty] == 0)
+        assert np.array_equal(g[~is_empty], g0) and np.array_equal(l[~is_empty], l0)
+    assert np.array_equal(g4, g0) and np.array_equal(l4, l0)
+
+
 def test_empty_and_invalid_worklists():
     w, _, _ = small_world(n_blocks=500)
     with ChainScorer(0) as sc:
