@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--qchroms", type=int, default=8, help="mm10 chromosomes the chains land on")
     ap.add_argument("--keep", default=None)
     ap.add_argument("--tools", default="scoreChain", help="comma list of scoreChain,chainNet,chainCleaner (configs[0..2] of BASELINE.json)")
+    ap.add_argument("--gpus-list", default="", help="comma list of N: also time bin/scoreChain -gpus=N (N above the box's GPU count "
+                    "runs several contexts per device through GAT_DEVICES) and report each shard's host->device bytes")
     args = ap.parse_args()
     ex = os.path.join(ROOT, "tests", "golden", "example")
     tn, ts = synth.read_chrom_sizes(os.path.join(ex, "hg38.chrom.sizes"))
@@ -87,6 +89,30 @@ def main():
                       "speedup": round(t_ref / t_ours, 2), "outputs_identical": bool(same), "ours_phases_s": phase_s}))
     if not same:
         raise SystemExit("outputs differ")
+    if args.gpus_list:
+        import torch
+        have = torch.cuda.device_count()
+        for n in [int(x) for x in args.gpus_list.split(",")]:
+            env = dict(os.environ, GAT_TOOL_TIMING="1")
+            if n > have:
+                env["GAT_DEVICES"] = ",".join(str(i % have) for i in range(n))
+            out_n = os.path.join(d, "ours.gpus%d.chain" % n)
+            cmd = [ours] + common + [out_n, "-linearGap=medium", "-gpus=%d" % n]
+            walls, err = [], ""
+            for _ in range(3):
+                t0 = time.time()
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+                walls.append(time.time() - t0)
+                if r.returncode != 0:
+                    sys.stderr.write(r.stderr.decode()[-2000:])
+                    raise SystemExit("scoreChain -gpus=%d failed" % n)
+                err = r.stderr.decode()
+            shards = [l for l in err.splitlines() if l.startswith("gpu shard")]
+            h2d = [int(l.split(" bytes host->device")[0].split()[-1]) for l in shards]
+            phase_s = {" ".join(l.split()[1:-2]): float(l.split()[-2]) for l in err.splitlines() if l.startswith("[timing]")}
+            print(json.dumps({"tool": "scoreChain -gpus=%d" % n, "devices": env.get("GAT_DEVICES", "0..%d" % (n - 1)), "blocks": int(w.total),
+                              "ours_wall_s": round(min(walls), 2), "outputs_identical": bool(filecmp.cmp(out_ref, out_n, shallow=False)),
+                              "h2d_bytes_per_shard": h2d, "h2d_bytes_total": sum(h2d), "phases_s": phase_s}))
     tools = args.tools.split(",")
     if "chainNet" in tools or "chainCleaner" in tools:
         refdir, ourdir = os.path.join(ROOT, "oracle", "_ref"), os.path.join(ROOT, "bin")
