@@ -15,6 +15,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
+#include <chrono>
 #include <thread>
 #include <tuple>
 #include <unistd.h>
@@ -1339,21 +1340,40 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
         else for (uint64_t r = 0; r < p.count; r++) bases += wl.blocks[p.first + r].size & 0x7fffffffu;
         p.weight = bases + 64 * (int64_t)p.count + 64;      // short blocks cost more per base than long ones
     }
-    // ---- greedy longest-processing-time balance of the pieces
-    std::vector<uint32_t> order(pieces.size());
+    // ---- greedy longest-processing-time balance, over units: a heavy piece is a unit of its own, light pieces go in runs of
+    // neighbours in file order (neighbours share genome sectors, and a few hundred units sort and balance in no time where
+    // a million pieces do not)
+    int64_t allWeight = 0;
+    for (const Piece &p : pieces) allWeight += p.weight;
+    const int64_t heavy = std::max<int64_t>(1, allWeight / (64 * (int64_t)nGpus));
+    struct Unit { uint32_t first, count; int64_t weight; };
+    std::vector<Unit> units;
+    for (uint32_t i = 0; i < pieces.size();) {
+        Unit u{i, 1, pieces[i].weight};
+        i++;
+        if (u.weight < heavy)
+            while (i < pieces.size() && pieces[i].weight < heavy && u.weight + pieces[i].weight <= heavy) { u.weight += pieces[i].weight; u.count++; i++; }
+        units.push_back(u);
+    }
+    std::vector<uint32_t> order(units.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pieces[a].weight > pieces[b].weight; });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return units[a].weight > units[b].weight; });
     typedef std::pair<int64_t, int> Load;
     std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
     for (size_t g = 0; g < nGpus; g++) heap.push(Load(0, (int)g));
-    std::vector<std::vector<uint32_t>> shard(nGpus);
-    for (uint32_t pi : order) {
+    std::vector<std::vector<uint32_t>> shardUnits(nGpus);
+    for (uint32_t ui : order) {
         Load l = heap.top();
         heap.pop();
-        shard[l.second].push_back(pi);
-        heap.push(Load(l.first + pieces[pi].weight, l.second));
+        shardUnits[l.second].push_back(ui);
+        heap.push(Load(l.first + units[ui].weight, l.second));
     }
-    for (auto &v : shard) std::sort(v.begin(), v.end());        // file order inside a shard: neighbours share sectors
+    std::vector<std::vector<uint32_t>> shard(nGpus);
+    for (size_t g = 0; g < nGpus; g++) {
+        std::sort(shardUnits[g].begin(), shardUnits[g].end());  // file order inside a shard
+        for (uint32_t ui : shardUnits[g])
+            for (uint32_t k = 0; k < units[ui].count; k++) shard[g].push_back(units[ui].first + k);
+    }
 
     // ---- one host thread per GPU: compact the shard's records, stage them in pinned memory, score
     std::vector<int64_t> pGlobal(pieces.size()), pLocal(pieces.size());
@@ -1365,6 +1385,8 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
             try {
                 const std::vector<uint32_t> &mine = shard[g];
                 if (mine.empty()) return;
+                const auto t0 = std::chrono::steady_clock::now();
+                auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
                 WorkList sw;            // the shard as a work-list of its own: records copied range by range
                 sw.jobs.resize(mine.size());
                 uint64_t total = 0;
@@ -1390,7 +1412,10 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
                     fail("%s", gat_last_error());
                 CompactWorkList cw;
                 int rc;
-                if (packCompact(sw, cw)) {
+                const bool packed = packCompact(sw, cw);
+                st.buildS = since(t0);
+                const auto t1 = std::chrono::steady_clock::now();
+                if (packed) {
                     const size_t bj = cw.jobs.size() * sizeof(gat_cjob), bb = cw.blocks.size() * sizeof(gat_cblock),
                                  ba = cw.abs.size() * sizeof(gat_cabs), bn = cw.anchors.size() * sizeof(gat_cabs);
                     auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
@@ -1398,6 +1423,7 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
                     char *pj = base, *pb = pj + up(bj), *pa = pb + up(bb), *pn = pa + up(ba);
                     memcpy(pj, cw.jobs.data(), bj); memcpy(pb, cw.blocks.data(), bb); memcpy(pa, cw.abs.data(), ba); memcpy(pn, cw.anchors.data(), bn);
                     st.compact = true; st.h2dBytes = bj + bb + ba + bn;
+                    st.stageS = since(t1);
                     rc = gat_score_compact(ctx[g], reinterpret_cast<gat_cjob *>(pj), cw.jobs.size(), reinterpret_cast<gat_cblock *>(pb), cw.blocks.size(),
                                            reinterpret_cast<gat_cabs *>(pa), cw.abs.size(), reinterpret_cast<gat_cabs *>(pn), gl.data(), lo.data());
                 } else {
@@ -1406,10 +1432,12 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
                     char *pj = base, *pb = base + ((bj + 63) & ~(size_t)63);
                     memcpy(pj, sw.jobs.data(), bj); memcpy(pb, sw.blocks.data(), bb);
                     st.h2dBytes = bj + bb;
+                    st.stageS = since(t1);
                     rc = gat_score(ctx[g], reinterpret_cast<gat_job *>(pj), sw.jobs.size(), total, reinterpret_cast<gat_block *>(pb), sw.blocks.size(),
                                    gl.data(), lo.data());
                 }
                 if (rc != GAT_OK) fail("%s", gat_last_error());
+                st.scoreS = since(t1) - st.stageS;
                 for (size_t k = 0; k < mine.size(); k++) { pGlobal[mine[k]] = gl[k]; pLocal[mine[k]] = lo[k]; }
                 for (size_t k = 0; k < wantTuple.size(); k++) pTuple[mine[wantTuple[k]]] = tup[k];
             } catch (const Error &e) { errors[g] = e.message; }
@@ -1420,9 +1448,11 @@ void MultiGpu::score(const WorkList &wl, std::vector<int64_t> &global, std::vect
 
     if (getenv("GAT_TOOL_TIMING"))
         for (size_t g = 0; g < nGpus; g++)
-            fprintf(stderr, "gpu shard %zu: %llu jobs, %llu records, %llu bytes host->device (%s), %llu pieces of cut chains\n", g,
+            fprintf(stderr, "gpu shard %zu: %llu jobs, %llu records, %llu bytes host->device (%s), %llu pieces of cut chains; host: build %.3f s, stage %.3f s, "
+                    "scoring call %.3f s\n", g,
                     (unsigned long long)lastShards[g].jobs, (unsigned long long)lastShards[g].records, (unsigned long long)lastShards[g].h2dBytes,
-                    lastShards[g].compact ? "compact" : "plain", (unsigned long long)lastShards[g].pieces);
+                    lastShards[g].compact ? "compact" : "plain", (unsigned long long)lastShards[g].pieces, lastShards[g].buildS, lastShards[g].stageS,
+                    lastShards[g].scoreS);
     // ---- back to jobs; the pieces of a cut chain are joined in order with the gap cost between them
     for (size_t j = 0; j < nJobs; j++) {
         const uint32_t p0 = firstPiece[j], p1 = firstPiece[j + 1];

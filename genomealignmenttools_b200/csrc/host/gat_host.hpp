@@ -166,7 +166,8 @@ struct MultiGpu {
     void prepare(const TwoBitFile &tbT, const std::vector<int> &useT, const TwoBitFile &tbQ, const std::vector<int> &useQ,
                  const ScoreScheme &ss, const GapCalc &gc);
     void score(const WorkList &wl, std::vector<int64_t> &global, std::vector<int64_t> &local);
-    struct ShardStats { uint64_t jobs = 0, records = 0, h2dBytes = 0, pieces = 0; bool compact = false; };
+    struct ShardStats { uint64_t jobs = 0, records = 0, h2dBytes = 0, pieces = 0; bool compact = false;
+                        double buildS = 0, stageS = 0, scoreS = 0; };   // host seconds: shard's work-list, pinned staging, the scoring call
     std::vector<ShardStats> lastShards;     // what the last score() sent to each GPU (tests, -verbose)
     // GAT_DUMP_WORKLIST=<prefix> in the environment: every score() call also writes its work-list to <prefix>.<k>.jobs / .blocks
     // (raw gat_job / gat_block arrays) and the sequence names in upload order to <prefix>.tseqs / .qseqs, so that bench.py can

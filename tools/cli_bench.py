@@ -109,10 +109,12 @@ def main():
                 err = r.stderr.decode()
             shards = [l for l in err.splitlines() if l.startswith("gpu shard")]
             h2d = [int(l.split(" bytes host->device")[0].split()[-1]) for l in shards]
+            host_s = [[float(x.split()[-2]) for x in l.split("host:")[1].split(",")] for l in shards if "host:" in l]
             phase_s = {" ".join(l.split()[1:-2]): float(l.split()[-2]) for l in err.splitlines() if l.startswith("[timing]")}
             print(json.dumps({"tool": "scoreChain -gpus=%d" % n, "devices": env.get("GAT_DEVICES", "0..%d" % (n - 1)), "blocks": int(w.total),
                               "ours_wall_s": round(min(walls), 2), "outputs_identical": bool(filecmp.cmp(out_ref, out_n, shallow=False)),
-                              "h2d_bytes_per_shard": h2d, "h2d_bytes_total": sum(h2d), "phases_s": phase_s}))
+                              "h2d_bytes_per_shard": h2d, "h2d_bytes_total": sum(h2d),
+                              "host_s_per_shard_build_stage_score": host_s, "phases_s": phase_s}))
     tools = args.tools.split(",")
     if "chainNet" in tools or "chainCleaner" in tools:
         refdir, ourdir = os.path.join(ROOT, "oracle", "_ref"), os.path.join(ROOT, "bin")
