@@ -451,9 +451,10 @@ extern "C" void gat_worklist_destroy(gat_ctx *ctx, gat_worklist *wl)
     delete wl;
 }
 
-// Which instantiation scores the list: the one that streams long blocks pays about 3 % on short-block lists and gains up
-// to 40 % on long-block ones (gat_tiles.cuh, streamLongBlocks).  A sample of at most 4096 record sizes, evenly spread,
-// decides: stream when blocks of more than 1056 bases hold at least an eighth of the sampled bases.  Both instantiations
+// Which instantiation scores the list: the one that streams long blocks pays 3 to 7 % on short-block lists and gains up
+// to 60 % on long-block ones (gat_tiles.cuh, streamLongBlocks).  A sample of at most 4096 record sizes, evenly spread,
+// decides: stream when blocks of more than 1056 bases hold at least a fifth of the sampled bases (about where the gain on
+// the long blocks meets the cost on the short ones).  Both instantiations
 // score every list exactly; this is about speed only.
 template <typename Rec>
 static bool pickLong(const Rec *recs, uint64_t n, uint32_t sizeMask)
@@ -466,7 +467,7 @@ static bool pickLong(const Rec *recs, uint64_t n, uint32_t sizeMask)
         all += size;
         if (size > 1056u) inLong += size;
     }
-    return inLong * 8 >= all && inLong > 0;
+    return inLong * 5 >= all && inLong > 0;
 }
 
 static int uploadWorklist(gat_ctx *ctx, gat_worklist *wl, const gat_job *jobs, const gat_block *blocks)

@@ -258,7 +258,7 @@ __device__ __forceinline__ void warpJobReduce32(const ScoreParams &P, const uint
 //
 // Why a template parameter and not one kernel: the per-block path (phase 1 unrolled four times) is as large as the SM's
 // instruction cache takes -- with this loop behind it warps wait for instruction fetches (no_instruction 0.22 -> 1.84 per
-// issue, +17 % kernel time at 67-base blocks, profiles/README.md).  So the LONG instantiations run phase 1 as a loop (+3 %
+// issue, +17 % kernel time at 67-base blocks, profiles/README.md).  So the LONG instantiations run phase 1 as a loop (+3 to 7 %
 // at 67-base blocks) and stream long blocks, four steps in flight (9-kb blocks: 0.42 -> 0.67 of the HBM roofline; two steps: 0.58); the others list every block as
 // before.  The host picks per work-list from a sample of the block sizes (gat_capi.cu: pickLong).
 constexpr uint32_t LONG_BASES = 32 + 1024;
