@@ -48,6 +48,10 @@ static int toolMain(int argc, char **argv)
     for (const std::string &m : cs.metaLines) fprintf(f, "%s\n", m.c_str());      // lineFileSetMetaDataOutput
     std::vector<size_t> order(cs.chains.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = order.size() - 1 - i;     // slAddHead: last chain first
+    // Tie order (chains with equal keys): kent's slSort is libc qsort over the list that slAddHead reversed.  glibc's qsort is a
+    // stable merge sort whenever it can allocate its buffer (every version the reference's fixtures were made with, up to 2.36),
+    // which std::stable_sort over the reversed order reproduces; glibc 2.37+ may use introsort, whose tie order is unspecified
+    // -- against a reference built there, equal-score chains can come out in another order.
     const auto &ch = cs.chains;
     if (isTarget)
         std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
