@@ -7,7 +7,7 @@ synthetic hg38 x mm10 chain set -- all 455 / 66 sequences of example/{hg38,mm10}
 with the default matrix and -linearGap=medium (global + local score per chain, as scoreChain does).
 
 A step = one pass of the hot path over the rank's whole work-list.  `value` times the kernels with
-the work-list resident in HBM; `e2e` times the public call gat_score_compact() with pinned HOST buffers
+the work-list resident in HBM; `e2e` times the public call gat_score_packed() with pinned HOST buffers
 (H2D of the work-list + kernels + D2H of the scores) every step.  At N > 1 the SAME ~10 M-block set is cut
 N ways (strong scaling, the default): chains above 1/(4N) of the aligned bases are cut at block boundaries
  and the pieces are balanced over the GPUs by greedy aligned-base load; every GPU holds a full
@@ -498,11 +498,32 @@ def main():
             e2e_tuples[0] = sc.request_tuples(part_local)
         sc.score_compact(pins[0].array, pins[1].array, pins[2].array, pins[3].array, pg.array, pl.array)
 
-    e2e_ms = time_calls(compact_call)
+    compact_ms = time_calls(compact_call)
     assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "compact e2e and resident results differ"
     assert part_tuples is None or np.array_equal(e2e_tuples[0], part_tuples), "compact e2e and resident tuples differ"
-    compact_bytes = int(cj.nbytes + cb.nbytes + ab.nbytes + an.nbytes)
-    h2d_ms, kern_ms = parts_of(compact_call)
+    compact6_bytes = int(cj.nbytes + cb.nbytes + ab.nbytes + an.nbytes)
+    for pin in pins:
+        pin.free()
+
+    # headline: gat_score_packed(), one 32-bit word per block (size, gap in front on both sequences), absolute records for
+    # chain starts and gaps that do not fit
+    from genomealignmenttools_b200.records import pack_packed
+    packed = pack_packed(w.jobs, w.total, w.blocks)
+    pins = [PinnedArray(len(a), d) for a, d in zip(packed, (CJOB_DTYPE, np.uint32, CABS_DTYPE, CABS_DTYPE, np.uint32))]
+    for pin, a in zip(pins, packed):
+        pin.array[:] = a
+    pg.array[:] = 0; pl.array[:] = 0
+
+    def packed_call():
+        if len(part_local):
+            e2e_tuples[0] = sc.request_tuples(part_local)
+        sc.score_packed(pins[0].array, pins[1].array, pins[2].array, pins[3].array, pins[4].array, pg.array, pl.array)
+
+    e2e_ms = time_calls(packed_call)
+    assert np.array_equal(pg.array, g_res) and np.array_equal(pl.array, l_res), "packed e2e and resident results differ"
+    assert part_tuples is None or np.array_equal(e2e_tuples[0], part_tuples), "packed e2e and resident tuples differ"
+    compact_bytes = int(sum(a.nbytes for a in packed))
+    h2d_ms, kern_ms = parts_of(packed_call)
     # (a profiled call runs unsliced on one stream; the timed calls overlap the copy of a slice with the kernels of the one before)
     e2e_parts = {"h2d_and_expand_ms_unsliced": round(h2d_ms, 4), "kernels_ms_unsliced": round(kern_ms, 4)}
     clocks = sampler.stop(t_begin, t_end) if sampler else None
@@ -533,14 +554,14 @@ def main():
             log("scaling check: %s" % scaling_check)
 
     per_step_ms = ms / args.steps
-    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes()), plain_ms, ceiling],
+    stats = torch.tensor([per_step_ms, e2e_ms, kernel_ms, float(w.aligned_bp), float(w.algorithmic_bytes()), plain_ms, ceiling, compact_ms],
                          dtype=torch.float64, device="cuda")
     alg_bytes = float(w.algorithmic_bytes())
     ceiling_sum = ceiling
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        per_step_ms, e2e_ms, kernel_ms, plain_ms = mx[0].item(), mx[1].item(), mx[2].item(), mx[5].item()
+        per_step_ms, e2e_ms, kernel_ms, plain_ms, compact_ms = mx[0].item(), mx[1].item(), mx[2].item(), mx[5].item(), mx[7].item()
         total_bp = sm[3].item()
         alg_bytes = sm[4].item() / world          # per GPU (mean) against the slowest GPU's kernel time
         ceiling_sum = sm[6].item()
@@ -576,7 +597,9 @@ def main():
                     # bare copy of the step's bytes at that rate would take
                     "h2d_ceiling_gbs_all_ranks": round(ceiling_sum, 1), "h2d_ceiling_gbs_rank0": round(ceiling, 1),
                     "h2d_time_fraction_of_step": round((compact_bytes / (ceiling * 1e9)) / (e2e_ms * 1e-3), 3),
-                    "call": "gat_score_compact: work-list as a .chain file stores it (6-byte size/gap blocks, 8-byte chains), expanded on the device",
+                    "call": "gat_score_packed: work-list as a .chain file stores it (size and the gaps in front, one 32-bit word per block; 8-byte chains; absolute table for chain starts and gaps above 511), expanded on the device",
+                    "compact_records": {"call": "gat_score_compact: 6-byte size/gap blocks", "value": total_bp / (compact_ms * 1e-3) / 1e9,
+                                        "ms_per_step": compact_ms, "h2d_bytes_per_step": compact6_bytes},
                     "plain_records": {"call": "gat_score: 12-byte absolute blocks, 24-byte jobs", "value": total_bp / (plain_ms * 1e-3) / 1e9,
                                       "ms_per_step": plain_ms, "h2d_bytes_per_step": plain_bytes}},
             "gpu_launches": int(launches),

@@ -12,7 +12,7 @@ SYMBOLS = [
     "gat_last_error", "gat_device_count", "gat_create", "gat_destroy", "gat_load_genome",
     "gat_set_scoring", "gat_score", "gat_worklist_create", "gat_worklist_run", "gat_worklist_results",
     "gat_worklist_destroy", "gat_synchronize", "gat_get_stats", "gat_set_profiling",
-    "gat_host_alloc", "gat_host_free", "gat_max_record_bases", "gat_crossover", "gat_score_compact",
+    "gat_host_alloc", "gat_host_free", "gat_max_record_bases", "gat_crossover", "gat_score_compact", "gat_score_packed",
     "gat_request_tuples", "gat_tuple_join", "gat_tuple_scores", "gat_gap_cost",
 ]
 
@@ -60,6 +60,7 @@ def load():
     lib.gat_worklist_destroy.restype = None
     lib.gat_crossover.argtypes = [vp, vp, u64, vp, vp]
     lib.gat_score_compact.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
+    lib.gat_score_packed.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.gat_gap_cost.argtypes = [vp, vp, vp, u64, vp]
     lib.gat_request_tuples.argtypes = [vp, vp, u64, vp]
     lib.gat_tuple_join.argtypes = [vp, ctypes.c_int64, vp]

@@ -470,6 +470,19 @@ static bool pickLong(const Rec *recs, uint64_t n, uint32_t sizeMask)
     return inLong * 5 >= all && inLong > 0;
 }
 
+static bool pickLongWords(const gat_pblock *recs, uint64_t n)
+{
+    if (!recs || n == 0) return false;
+    const uint64_t step = n > 4096 ? n / 4096 : 1;
+    uint64_t all = 0, inLong = 0;
+    for (uint64_t i = 0; i < n; i += step) {
+        const uint32_t size = recs[i] & GAT_PBLOCK_MAX_SIZE;
+        all += size;
+        if (size > 1056u) inLong += size;
+    }
+    return inLong * 5 >= all && inLong > 0;
+}
+
 static int uploadWorklist(gat_ctx *ctx, gat_worklist *wl, const gat_job *jobs, const gat_block *blocks)
 {
     if (wl->nJobs) CU(cudaMemcpyAsync(wl->jobs, jobs, wl->nJobs * sizeof(gat_job), cudaMemcpyHostToDevice, ctx->stream));
@@ -737,14 +750,17 @@ extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint
     return rc;
 }
 
-extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_cblock *blocks, uint64_t nBlocks,
-                                 const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, int64_t *global, int64_t *local)
+// gat_score_compact (6-byte gat_cblock records, absBase == NULL) and gat_score_packed (4-byte gat_pblock words)
+static int scoreDeltaCoded(gat_ctx *ctx, const char *who, const gat_cjob *jobs, uint64_t nJobs, const void *blocksV, size_t recBytes, uint64_t nBlocks,
+                           const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, const uint32_t *absBase, int64_t *global, int64_t *local)
 {
-    if (!ctx) return fail(GAT_EINVAL, "gat_score_compact: NULL ctx");
-    if ((nJobs && (!jobs || !global || !local)) || (nBlocks && (!blocks || !anchors)) || (nAbs && !abs))
-        return fail(GAT_EINVAL, "gat_score_compact: NULL array");
-    if (!ctx->genome[0].loaded || !ctx->genome[1].loaded) return fail(GAT_ESTATE, "gat_score_compact: load both genomes first");
-    if (!ctx->scoringSet) return fail(GAT_ESTATE, "gat_score_compact: call gat_set_scoring first");
+    const bool packed = recBytes == sizeof(gat_pblock);
+    const char *blocks = static_cast<const char *>(blocksV);
+    if (!ctx) return fail(GAT_EINVAL, "%s: NULL ctx", who);
+    if ((nJobs && (!jobs || !global || !local)) || (nBlocks && (!blocks || !anchors || (packed && !absBase))) || (nAbs && !abs))
+        return fail(GAT_EINVAL, "%s: NULL array", who);
+    if (!ctx->genome[0].loaded || !ctx->genome[1].loaded) return fail(GAT_ESTATE, "%s: load both genomes first", who);
+    if (!ctx->scoringSet) return fail(GAT_ESTATE, "%s: call gat_set_scoring first", who);
     if (nJobs == 0) return GAT_OK;
     CU(cudaSetDevice(ctx->device));
     if (!ctx->scratch) ctx->scratch = new gat_worklist();
@@ -753,12 +769,15 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     if (rc != GAT_OK) return rc;
     wl->plain = 1;              // whole chains by construction
     wl->searchJobs = false;
-    wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0 : pickLong(blocks, nBlocks, GAT_CBLOCK_MAX_SIZE);
+    wl->streamLong = ctx->forceLong >= 0 ? ctx->forceLong != 0
+                     : packed ? pickLongWords(reinterpret_cast<const gat_pblock *>(blocks), nBlocks)
+                              : pickLong(reinterpret_cast<const gat_cblock *>(blocks), nBlocks, GAT_CBLOCK_MAX_SIZE);
     cudaStream_t st = ctx->stream;
     const uint64_t nGroups = (nBlocks + GAT_CGROUP - 1) / GAT_CGROUP;
     auto up8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    const size_t oJobs = 0, oBlocks = oJobs + up8(nJobs * sizeof(gat_cjob)), oAbs = oBlocks + up8(nBlocks * sizeof(gat_cblock) + 8),
-                 oAnch = oAbs + up8(nAbs * sizeof(gat_cabs)), need = oAnch + up8(nGroups * sizeof(gat_cabs)) + 16;
+    const size_t oJobs = 0, oBlocks = oJobs + up8(nJobs * sizeof(gat_cjob)), oAbs = oBlocks + up8(nBlocks * recBytes + 8),
+                 oAnch = oAbs + up8(nAbs * sizeof(gat_cabs)), oBase = oAnch + up8(nGroups * sizeof(gat_cabs)),
+                 need = oBase + up8(packed ? nGroups * sizeof(uint32_t) : 0) + 16;
     if (need > ctx->compactCap) {
         CU(cudaStreamSynchronize(st));
         cudaFree(ctx->compactBuf);
@@ -768,8 +787,13 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     }
     char *base = static_cast<char *>(ctx->compactBuf);
     const gat_cjob *dJobs = reinterpret_cast<const gat_cjob *>(base + oJobs);
-    const gat_cblock *dBlocks = reinterpret_cast<const gat_cblock *>(base + oBlocks);
+    const void *dBlocks = base + oBlocks;
     const gat_cabs *dAbs = reinterpret_cast<const gat_cabs *>(base + oAbs), *dAnch = reinterpret_cast<const gat_cabs *>(base + oAnch);
+    const uint32_t *dBase = packed ? reinterpret_cast<const uint32_t *>(base + oBase) : nullptr;
+    auto expand = [&](unsigned groups, unsigned firstGroup) {
+        if (packed) expandBlocksKernel<true><<<groups, CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, dBase, wl->blocks, firstGroup, ctx->err);
+        else expandBlocksKernel<false><<<groups, CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, dBase, wl->blocks, firstGroup, ctx->err);
+    };
     const bool prof = ctx->profiling;
     ctx->stats.chunks = wl->nChunks;
     ctx->stats.long_streamed = wl->streamLong ? 1u : 0u;
@@ -786,6 +810,7 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
     CU(cudaMemcpyAsync(base + oJobs, jobs, nJobs * sizeof(gat_cjob), cudaMemcpyHostToDevice, cp));
     if (nAbs) CU(cudaMemcpyAsync(base + oAbs, abs, nAbs * sizeof(gat_cabs), cudaMemcpyHostToDevice, cp));
     if (nGroups) CU(cudaMemcpyAsync(base + oAnch, anchors, nGroups * sizeof(gat_cabs), cudaMemcpyHostToDevice, cp));
+    if (packed && nGroups) CU(cudaMemcpyAsync(base + oBase, absBase, nGroups * sizeof(uint32_t), cudaMemcpyHostToDevice, cp));
     if (slices > 1) { CU(cudaEventRecord(ctx->sliceEv[COMPACT_SLICES], cp)); CU(cudaStreamWaitEvent(st, ctx->sliceEv[COMPACT_SLICES], 0)); }
     expandJobsKernel<<<(unsigned)((nJobs + 255) / 256), 256, 0, st>>>(dJobs, nJobs, wl->jobs);
     ctx->stats.kernel_launches = 0;
@@ -797,8 +822,8 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
         if (rc != GAT_OK) return rc;
         const ScoreParams P = scoreParams(ctx, wl);
         if (slices == 1) {
-            CU(cudaMemcpyAsync(base + oBlocks, blocks, nBlocks * sizeof(gat_cblock), cudaMemcpyHostToDevice, st));
-            expandBlocksKernel<<<(unsigned)nGroups, CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, 0, ctx->err);
+            CU(cudaMemcpyAsync(base + oBlocks, blocks, nBlocks * recBytes, cudaMemcpyHostToDevice, st));
+            expand((unsigned)nGroups, 0);
             if (prof) CU(cudaEventRecord(ctx->ev[0], st));
             rc = launchPrep(ctx, wl, st);
             if (rc != GAT_OK) return rc;
@@ -814,10 +839,10 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
                 const uint64_t g0 = s * groupsPerSlice, g1 = std::min<uint64_t>(nGroups, g0 + groupsPerSlice);
                 if (g0 >= g1) break;
                 const uint64_t r0 = g0 * GAT_CGROUP, r1 = std::min<uint64_t>(nBlocks, g1 * GAT_CGROUP);
-                CU(cudaMemcpyAsync(base + oBlocks + r0 * sizeof(gat_cblock), blocks + r0, (r1 - r0) * sizeof(gat_cblock), cudaMemcpyHostToDevice, cp));
+                CU(cudaMemcpyAsync(base + oBlocks + r0 * recBytes, blocks + r0 * recBytes, (r1 - r0) * recBytes, cudaMemcpyHostToDevice, cp));
                 CU(cudaEventRecord(ctx->sliceEv[s], cp));
                 CU(cudaStreamWaitEvent(st, ctx->sliceEv[s], 0));
-                expandBlocksKernel<<<(unsigned)(g1 - g0), CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, wl->blocks, (unsigned)g0, ctx->err);
+                expand((unsigned)(g1 - g0), (unsigned)g0);
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
                 launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, wl->searchJobs, false, st);      // (behind expandBlocksKernel: no early start)
                 sliceLaunches += 2;
@@ -835,10 +860,22 @@ extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJ
         float total = 0;
         cudaEventElapsedTime(&total, ctx->ev[4], ctx->ev[0]);
         ctx->stats.h2d_ms = total;          // copies + the two expansion kernels
-        ctx->stats.h2d_bytes = nJobs * sizeof(gat_cjob) + nBlocks * sizeof(gat_cblock) + nAbs * sizeof(gat_cabs) + nGroups * sizeof(gat_cabs);
+        ctx->stats.h2d_bytes = nJobs * sizeof(gat_cjob) + nBlocks * recBytes + nAbs * sizeof(gat_cabs) + nGroups * (sizeof(gat_cabs) + (packed ? sizeof(uint32_t) : 0));
         ctx->stats.d2h_bytes = 2 * nJobs * sizeof(long long);
     }
     return rc;
+}
+
+extern "C" int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_cblock *blocks, uint64_t nBlocks,
+                                 const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, int64_t *global, int64_t *local)
+{
+    return scoreDeltaCoded(ctx, "gat_score_compact", jobs, nJobs, blocks, sizeof(gat_cblock), nBlocks, abs, nAbs, anchors, nullptr, global, local);
+}
+
+extern "C" int gat_score_packed(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_pblock *blocks, uint64_t nBlocks,
+                                const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, const uint32_t *absBase, int64_t *global, int64_t *local)
+{
+    return scoreDeltaCoded(ctx, "gat_score_packed", jobs, nJobs, blocks, sizeof(gat_pblock), nBlocks, abs, nAbs, anchors, absBase, global, local);
 }
 
 extern "C" int gat_crossover(gat_ctx *ctx, const gat_xpair *pairs, uint64_t nPairs, int32_t *pos, int32_t *adjust)

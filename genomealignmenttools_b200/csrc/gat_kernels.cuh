@@ -705,25 +705,55 @@ constexpr int CX_TPB = GAT_CGROUP / 4;
 struct CxSeg { int t, q; bool abs; };       // start of the last record seen (abs) or sum of the steps so far
 __device__ __forceinline__ CxSeg cxCombine(const CxSeg &l, const CxSeg &r) { return r.abs ? r : CxSeg{l.t + r.t, l.q + r.q, l.abs}; }
 
+// PACKED (gat_score_packed): the records are gat_pblock words (4 bytes: size 12 bits, JOINED, ABS, dt and dq 9 bits each) and
+// an absolute record takes the next entry of the absolute table in list order: its index is absBase[group] + the number of
+// absolute records in front of it in the group (one more prefix count), so no index is stored.
+template <bool PACKED>
 __global__ void __launch_bounds__(CX_TPB)
-expandBlocksKernel(const gat_cblock *__restrict__ cb, unsigned long long nBlocks, const gat_cabs *__restrict__ absTab,
-                   unsigned long long nAbs, const gat_cabs *__restrict__ anchors, gat_block *__restrict__ out, unsigned firstGroup,
-                   int *__restrict__ err)
+expandBlocksKernel(const void *__restrict__ recs, unsigned long long nBlocks, const gat_cabs *__restrict__ absTab,
+                   unsigned long long nAbs, const gat_cabs *__restrict__ anchors, const uint32_t *__restrict__ absBase,
+                   gat_block *__restrict__ out, unsigned firstGroup, int *__restrict__ err)
 {
     __shared__ CxSeg sWarp[CX_TPB / 32];
+    __shared__ uint32_t sWarpAbs[CX_TPB / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned group = blockIdx.x + firstGroup;                 // a launch may cover a slice of the groups
     const unsigned long long g0 = (unsigned long long)group * GAT_CGROUP, r0 = g0 + 4ull * tid;
     // my four records, and the size of the record in front of them (its end is where my first step starts)
-    uint32_t size[4], dt[4], dq[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const bool in = r0 + k < nBlocks;
-        const uint16_t *p = reinterpret_cast<const uint16_t *>(cb + (in ? r0 + k : 0));
-        size[k] = in ? __ldg(p) : 0u; dt[k] = in ? __ldg(p + 1) : 0u; dq[k] = in ? __ldg(p + 2) : 0u;
-    }
+    uint32_t size[4], dt[4], dq[4];     // size keeps the flags of gat_cblock (GAT_CBLOCK_ABS / JOINED) in both formats
     uint32_t prevSize = 0;
-    if (tid > 0 && r0 - 1 < nBlocks) prevSize = __ldg(reinterpret_cast<const uint16_t *>(cb + r0 - 1)) & GAT_CBLOCK_MAX_SIZE;
+    unsigned long long absIx = 0;       // PACKED: index of my first absolute record
+    if (PACKED) {
+        const uint32_t *pb = static_cast<const uint32_t *>(recs);
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + 3 < nBlocks) w = __ldg(reinterpret_cast<const uint4 *>(pb + r0));      // groups start on multiples of 1024 records
+        else { if (r0 < nBlocks) w.x = __ldg(pb + r0); if (r0 + 1 < nBlocks) w.y = __ldg(pb + r0 + 1); if (r0 + 2 < nBlocks) w.z = __ldg(pb + r0 + 2); }
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            size[k] = (ws[k] & GAT_PBLOCK_MAX_SIZE) | ((ws[k] & GAT_PBLOCK_JOINED) ? GAT_CBLOCK_JOINED : 0u) | ((ws[k] & GAT_PBLOCK_ABS) ? GAT_CBLOCK_ABS : 0u);
+            dt[k] = (ws[k] >> 14) & 0x1ffu; dq[k] = ws[k] >> 23;
+            mine += (ws[k] & GAT_PBLOCK_ABS) ? 1u : 0u;
+        }
+        if (tid > 0 && r0 - 1 < nBlocks) prevSize = __ldg(pb + r0 - 1) & GAT_PBLOCK_MAX_SIZE;
+        uint32_t inc = mine;
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, off); if (lane >= off) inc += o; }
+        if (lane == 31) sWarpAbs[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w2 = 0; w2 < warp; w2++) before += sWarpAbs[w2];
+        absIx = (unsigned long long)__ldg(absBase + group) + before + inc - mine;
+    } else {
+        const gat_cblock *cb = static_cast<const gat_cblock *>(recs);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool in = r0 + k < nBlocks;
+            const uint16_t *p = reinterpret_cast<const uint16_t *>(cb + (in ? r0 + k : 0));
+            size[k] = in ? __ldg(p) : 0u; dt[k] = in ? __ldg(p + 1) : 0u; dq[k] = in ? __ldg(p + 2) : 0u;
+        }
+        if (tid > 0 && r0 - 1 < nBlocks) prevSize = __ldg(reinterpret_cast<const uint16_t *>(cb + r0 - 1)) & GAT_CBLOCK_MAX_SIZE;
+    }
     // per record: step from the previous record's start (or an absolute start); running fold inside the thread
     CxSeg rec[4];
     CxSeg acc{0, 0, false};
@@ -733,13 +763,14 @@ expandBlocksKernel(const gat_cblock *__restrict__ cb, unsigned long long nBlocks
         const bool first = tid == 0 && k == 0;
         if (first) { const gat_cabs a = anchors[group]; e = CxSeg{a.tStart, a.qStart, true}; }
         else if (size[k] & GAT_CBLOCK_ABS) {
-            const unsigned long long ix = (unsigned long long)dt[k] | ((unsigned long long)dq[k] << 16);
+            const unsigned long long ix = PACKED ? absIx : ((unsigned long long)dt[k] | ((unsigned long long)dq[k] << 16));
             if (ix < nAbs) { const gat_cabs a = absTab[ix]; e = CxSeg{a.tStart, a.qStart, true}; }
             else { atomicOr(err, ERR_BLOCKIDX); e = CxSeg{0, 0, true}; }
         } else {
             const int before = (int)(k == 0 ? prevSize : (size[k - 1] & GAT_CBLOCK_MAX_SIZE));
             e = CxSeg{before + (int)dt[k], before + (int)dq[k], false};
         }
+        if (PACKED && (size[k] & GAT_CBLOCK_ABS)) absIx++;        // (the group's first record skips its entry but owns one)
         acc = k == 0 ? e : cxCombine(acc, e);
         rec[k] = acc;                               // relative to whatever precedes the thread
     }

@@ -96,6 +96,18 @@ class ChainScorer:
                                                _ptr(anchors), _ptr(g), _ptr(l)))
         return g, l
 
+    def score_packed(self, cjobs, pblocks, ab, anchors, abs_base, out_global=None, out_local=None):
+        """gat_score_packed: the work-list as records.pack_packed() makes it (4 bytes per block)."""
+        from .records import CJOB_DTYPE, CABS_DTYPE
+        cjobs = np.ascontiguousarray(cjobs, dtype=CJOB_DTYPE); pblocks = np.ascontiguousarray(pblocks, dtype=np.uint32)
+        ab = np.ascontiguousarray(ab, dtype=CABS_DTYPE); anchors = np.ascontiguousarray(anchors, dtype=CABS_DTYPE)
+        abs_base = np.ascontiguousarray(abs_base, dtype=np.uint32)
+        g = out_global if out_global is not None else np.zeros(len(cjobs), dtype=np.int64)
+        l = out_local if out_local is not None else np.zeros(len(cjobs), dtype=np.int64)
+        self._check(self.lib.gat_score_packed(self.ctx, _ptr(cjobs), len(cjobs), _ptr(pblocks), len(pblocks), _ptr(ab), len(ab),
+                                              _ptr(anchors), _ptr(abs_base), _ptr(g), _ptr(l)))
+        return g, l
+
     def crossover(self, pairs):
         """cBlockFindCrossover (kent chainConnect.c:61-105) for a batch of overlapping block pairs (XPAIR_DTYPE):
         returns (pos, adjust) int32 arrays."""

@@ -129,6 +129,75 @@ def pack_compact(jobs, total_job_blocks, blocks):
     return cj, cb, ab, anchors
 
 
+# ---- 4-byte work-list of gat_score_packed (include/gat.h): gat_pblock words
+PBLOCK_MAX_SIZE, PBLOCK_JOINED, PBLOCK_ABS, PBLOCK_MAX_GAP = 0xFFF, 0x1000, 0x2000, 511
+
+
+def pack_packed(jobs, total_job_blocks, blocks):
+    """Whole-chain work-list -> (cjobs, pblocks, abs, anchors, abs_base) of gat_score_packed: one 32-bit word per block (size 12
+    bits, JOINED, ABS, dt and dq 9 bits each).  Blocks of more than 4095 bases are cut into JOINED pieces here; a block that opens a
+    chain or whose gap is negative or above 511 on either side takes the next entry of the absolute table (no index stored)."""
+    jobs, n, blocks = split_long_blocks(jobs, total_job_blocks, blocks, PBLOCK_MAX_SIZE)
+    jobs = np.asarray(jobs); blocks = np.asarray(blocks)
+    if n != len(blocks) or not np.array_equal(jobs["firstBlock"], jobs["blockPtr"]):
+        raise ValueError("pack_packed wants jobs that tile the block array")
+    if np.any(jobs["clipStart"] != NO_CLIP_START) or np.any(jobs["clipEnd"] != NO_CLIP_END):
+        raise ValueError("pack_packed wants unclipped jobs")
+    if np.any(jobs["tSeq"] > 0xFFFF) or np.any((jobs["qSeq"] & np.uint32(0x7FFFFFFF)) > 0x7FFF):
+        raise ValueError("pack_packed: sequence index beyond 16 bits")
+    size = (blocks["size"] & np.uint32(0x7FFFFFFF)).astype(np.int64)
+    joined = (blocks["size"] >> np.uint32(31)).astype(bool)
+    ts = blocks["tStart"].astype(np.int64); qs = blocks["qStart"].astype(np.int64)
+    dt = np.zeros(n, dtype=np.int64); dq = np.zeros(n, dtype=np.int64)
+    dt[1:] = ts[1:] - (ts[:-1] + size[:-1]); dq[1:] = qs[1:] - (qs[:-1] + size[:-1])
+    is_abs = (dt < 0) | (dt > PBLOCK_MAX_GAP) | (dq < 0) | (dq > PBLOCK_MAX_GAP)
+    counts = job_block_counts(jobs, n)
+    is_abs[jobs["blockPtr"][counts > 0].astype(np.int64)] = True      # first block of every chain
+    pb = (size | np.where(joined, PBLOCK_JOINED, 0) | np.where(is_abs, PBLOCK_ABS, 0)
+          | (np.where(is_abs, 0, dt) << 14) | (np.where(is_abs, 0, dq) << 23)).astype(np.uint32)
+    ab = np.zeros(int(is_abs.sum()), dtype=CABS_DTYPE)
+    ab["tStart"] = ts[is_abs]; ab["qStart"] = qs[is_abs]
+    n_groups = (n + CGROUP - 1) // CGROUP
+    anchors = np.zeros(n_groups, dtype=CABS_DTYPE)
+    anchors["tStart"] = ts[::CGROUP]; anchors["qStart"] = qs[::CGROUP]
+    before = np.concatenate([[0], np.cumsum(is_abs)])                 # absolute records in front of record i
+    abs_base = before[np.arange(n_groups) * CGROUP].astype(np.uint32)
+    cj = np.zeros(len(jobs), dtype=CJOB_DTYPE)
+    cj["blockPtr"] = jobs["blockPtr"]; cj["tSeq"] = jobs["tSeq"]
+    cj["qSeq"] = (jobs["qSeq"] & np.uint32(0x7FFF)) | np.where(jobs["qSeq"] >> np.uint32(31), CJOB_MINUS, 0).astype(np.uint32)
+    return cj, pb, ab, anchors, abs_base
+
+
+def unpack_packed(cjobs, pblocks, ab, anchors, abs_base):
+    """Host restatement of the device expansion of a packed list (tests) -> (jobs, total, blocks)."""
+    n = len(pblocks)
+    w = pblocks.astype(np.int64)
+    size = w & PBLOCK_MAX_SIZE
+    is_abs = (w & PBLOCK_ABS) != 0
+    dt = (w >> 14) & 0x1FF; dq = w >> 23
+    ts = np.zeros(n, dtype=np.int64); qs = np.zeros(n, dtype=np.int64)
+    k = 0
+    for i in range(n):
+        if i % CGROUP == 0:
+            k = int(abs_base[i // CGROUP])
+            ts[i], qs[i] = anchors["tStart"][i // CGROUP], anchors["qStart"][i // CGROUP]
+        elif is_abs[i]:
+            ts[i], qs[i] = ab["tStart"][k], ab["qStart"][k]
+        else:
+            ts[i] = ts[i - 1] + size[i - 1] + dt[i]; qs[i] = qs[i - 1] + size[i - 1] + dq[i]
+        if is_abs[i]:
+            k += 1
+    blocks = np.zeros(n, dtype=BLOCK_DTYPE)
+    blocks["tStart"] = ts; blocks["qStart"] = qs
+    blocks["size"] = size.astype(np.uint32) | np.where(w & PBLOCK_JOINED, BLOCK_JOINED, 0).astype(np.uint32)
+    jobs = np.zeros(len(cjobs), dtype=JOB_DTYPE)
+    jobs["tSeq"] = cjobs["tSeq"]
+    jobs["qSeq"] = (cjobs["qSeq"] & 0x7FFF).astype(np.uint32) | np.where(cjobs["qSeq"] & CJOB_MINUS, QSEQ_MINUS, 0).astype(np.uint32)
+    jobs["firstBlock"] = cjobs["blockPtr"]; jobs["blockPtr"] = cjobs["blockPtr"]
+    jobs["clipStart"] = NO_CLIP_START; jobs["clipEnd"] = NO_CLIP_END
+    return jobs, n, blocks
+
+
 def unpack_compact(cjobs, cblocks, ab, anchors):
     """Host restatement of the device expansion (tests): compact work-list -> (jobs, total, blocks)."""
     n = len(cblocks)

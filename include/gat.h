@@ -169,6 +169,21 @@ typedef struct gat_cabs { int32_t tStart, qStart; } gat_cabs;
 int gat_score_compact(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_cblock *blocks, uint64_t nBlocks,
                       const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, int64_t *global, int64_t *local);
 
+/* The same list in 4 bytes per block (gat_score_packed): what most records of a .chain file need.  gat_pblock is one word,
+ *   bits 0..11 size (<= GAT_PBLOCK_MAX_SIZE; longer blocks are cut into GAT_PBLOCK_JOINED pieces), bit 12 GAT_PBLOCK_JOINED,
+ *   bit 13 GAT_PBLOCK_ABS, bits 14..22 dt, bits 23..31 dq (the gap in front of the block, each <= 511).
+ * A block that opens a chain, or whose gap is negative or above 511 on either side, is absolute: it takes the NEXT entry of abs[] in
+ * list order (no index is stored: entry k belongs to the k-th absolute record of the list), and absBase[g] = number of absolute
+ * records in front of record 1024 * g lets the groups expand independently.  jobs, abs and anchors as in gat_score_compact.
+ * About 59 MB instead of 77 MB per 10 M blocks of a typical chain file; the scores are those of gat_score on the expanded list. */
+#define GAT_PBLOCK_MAX_SIZE 0xfffu
+#define GAT_PBLOCK_JOINED 0x1000u
+#define GAT_PBLOCK_ABS 0x2000u
+#define GAT_PBLOCK_MAX_GAP 511u
+typedef uint32_t gat_pblock;
+int gat_score_packed(gat_ctx *ctx, const gat_cjob *jobs, uint64_t nJobs, const gat_pblock *blocks, uint64_t nBlocks,
+                     const gat_cabs *abs, uint64_t nAbs, const gat_cabs *anchors, const uint32_t *absBase, int64_t *global, int64_t *local);
+
 /* Crossover points of overlapping adjacent blocks, in one batch: what kent's chainRemovePartialOverlaps asks of
  *     void cBlockFindCrossover(struct cBlock *left, struct cBlock *right, struct dnaSeq *qSeq, struct dnaSeq *tSeq,
  *                              int overlap, int matrix[256][256], int *retPos, int *retScoreAdjustment)

@@ -498,6 +498,36 @@ def test_compact_worklist_scores_like_plain(n_blocks, kw):
             assert np.array_equal(g, g2)
 
 
+@pytest.mark.parametrize("n_blocks,kw", [(9000, {}), (1024, dict(max_chain_blocks=5)), (3, dict(max_chain_blocks=2)), (2049, {}),
+                                         (30000, dict(gap_mu=6.0, gap_sigma=3.0, max_gap=900000, max_len=60000, mean_log_len=5.0)),
+                                         (1_200_000, dict(max_chain_blocks=400000))])
+def test_packed_worklist_scores_like_plain(n_blocks, kw):
+    """gat_score_packed (4-byte words, absolute records in list order, expanded on the device; sliced above a million blocks)
+    gives the scores of gat_score on the same chains."""
+    from genomealignmenttools_b200.records import pack_packed, PBLOCK_ABS
+    if n_blocks > 100000:
+        w = synth.make_workload(["chrA", "chrB"], [60_000_000, 9_000_000], ["chrX", "chrY"], [50_000_000, 8_000_000], n_blocks, seed=45,
+                                telomere_n=400, n_fraction=0.002, **kw)
+    else:
+        w, _, _ = small_world(seed=45, n_blocks=n_blocks, **kw)
+    blocks = w.blocks
+    if n_blocks == 9000:        # out-of-order blocks inside a chain: a negative gap is an absolute record
+        blocks = blocks.copy()
+        i = int(w.jobs["firstBlock"][np.argmax(job_block_counts(w.jobs, w.total))]) + 1
+        blocks["qStart"][i + 1] = blocks["qStart"][i] - 3
+    cj, pb, ab, an, base = pack_packed(w.jobs, w.total, blocks)
+    with ChainScorer(0) as sc:
+        sc.load_genome("t", w.t); sc.load_genome("q", w.q); sc.set_scoring(Scoring(None, "medium"))
+        g, l = sc.score(w.jobs, w.total, blocks)
+        pg, pl = sc.score_packed(cj, pb, ab, an, base)
+        assert np.array_equal(g, pg) and np.array_equal(l, pl)
+        if len(ab) > 1:         # a table that is too short is rejected, and the context survives
+            with pytest.raises(GatError):
+                sc.score_packed(cj, pb, ab[:-1], an, base)
+            g2, l2 = sc.score_packed(cj, pb, ab, an, base)
+            assert np.array_equal(g, g2) and np.array_equal(l, l2)
+
+
 def test_resident_worklist_matches_one_shot():
     w, _, _ = small_world(seed=12, n_blocks=9000)
     with ChainScorer(0) as sc:

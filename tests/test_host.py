@@ -204,6 +204,26 @@ def test_compact_worklist_roundtrip():
         pack_compact(*synth.make_chains([5_000_000], [4_000_000], 2000, seed=6, max_len=30000, mean_log_len=9.0))   # unsplit long blocks
 
 
+def test_packed_worklist_roundtrip():
+    """records.pack_packed (one 32-bit word per block, absolute records take the next table entry in list order, absBase per
+    group) expands back to the records cut at 4095 bases: chain starts, gaps beyond 9 bits, negative gaps, JOINED pieces,
+    empty blocks, groups that open with an absolute record."""
+    from genomealignmenttools_b200.records import pack_packed, unpack_packed, split_long_blocks, PBLOCK_ABS, CGROUP
+    jobs, total, blocks = synth.make_chains([5_000_000, 800_000], [4_000_000, 900_000], 20000, seed=5, max_chain_blocks=3000,
+                                            max_len=30000, gap_mu=6.0, gap_sigma=3.0, max_gap=900000)
+    blocks["tStart"][100], blocks["tStart"][101] = blocks["tStart"][101], blocks["tStart"][100]      # a negative gap
+    blocks["size"][200] = 0                                                                           # an empty block
+    cj, pb, ab, an, base = pack_packed(jobs, total, blocks)
+    j2, t2, b2 = unpack_packed(cj, pb, ab, an, base)
+    js, ts, bs = split_long_blocks(jobs, total, blocks, 4095)
+    assert np.array_equal(js, j2) and ts == t2 and np.array_equal(bs, b2)
+    assert len(ab) > len(jobs) and int(((pb & PBLOCK_ABS) != 0).sum()) == len(ab)
+    assert base[0] == 0 and np.all(np.diff(base.astype(np.int64)) >= 0) and len(base) == (t2 + CGROUP - 1) // CGROUP
+    jobs, total, blocks = synth.make_chains([50_000_000], [40_000_000], 200000, seed=9)               # typical gaps: 4 bytes pay
+    cj, pb, ab, an, base = pack_packed(jobs, total, blocks)
+    assert (cj.nbytes + pb.nbytes + ab.nbytes + an.nbytes + base.nbytes) < 0.45 * (jobs.nbytes + blocks.nbytes)
+
+
 def test_cpp_compact_packer_agrees_with_python(golden):
     """gathost::packCompact (what bin/scoreChain sends to gat_score_compact) == records.pack_compact on the same chains."""
     from genomealignmenttools_b200.records import (pack_compact, CJOB_DTYPE, CBLOCK_DTYPE, CABS_DTYPE, NO_CLIP_START, NO_CLIP_END,
