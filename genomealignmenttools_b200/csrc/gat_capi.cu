@@ -30,7 +30,10 @@ static int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(GAT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int COMPACT_SLICES = 4;
+#ifndef GAT_COMPACT_SLICES
+#define GAT_COMPACT_SLICES 8     // measured: 3 / 4 / 6 / 8 / 12 slices = 423 / 428 / 435 / 436 / 436 Gbp/s end to end at 10 M blocks
+#endif
+constexpr int COMPACT_SLICES = GAT_COMPACT_SLICES;
 static_assert(GAT_CGROUP % gat::CHUNK == 0, "a slice of record groups must be a whole number of chunks");
 
 struct GenomeDev {
