@@ -78,6 +78,8 @@ struct gat_ctx {
     size_t compactCap = 0;
     cudaStream_t copyStream = nullptr; // gat_score_compact(): slices are copied here while earlier ones are scored
     cudaEvent_t sliceEv[COMPACT_SLICES + 1] = {};
+    cudaStream_t backStream = nullptr;  // ... and the scores of the jobs that end in a slice are copied back here meanwhile
+    cudaEvent_t fixEv[COMPACT_SLICES] = {};
     uint32_t residentCtas = 0;         // scoring-kernel CTAs the device holds at once
     uint32_t maxBlockBases = GAT_MAX_BLOCK_BASES;   // longest record whose score surely fits 32 bits
     uint32_t smallBases = 1;
@@ -178,6 +180,7 @@ extern "C" void gat_destroy(gat_ctx *ctx)
     cudaFree(ctx->compactBuf);
     cudaFree(ctx->xoverBuf);
     if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); for (auto &e : ctx->sliceEv) cudaEventDestroy(e); }
+    if (ctx->backStream) { cudaStreamDestroy(ctx->backStream); for (auto &e : ctx->fixEv) cudaEventDestroy(e); }
     cudaFree(ctx->gapSmall); cudaFree(ctx->gapLongPos); cudaFree(ctx->gapLongVal); cudaFree(ctx->gapDense); cudaFree(ctx->err);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -611,12 +614,16 @@ static int launchScoring(gat_ctx *ctx, ScoreParams P, uint32_t first, uint32_t c
     return launches;
 }
 
-static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st)
+// chunks [0, upTo) are looked at, jobs that end in chunks [endLo, endHi) are finished; `last`: also clear the job-start bitmap
+static void launchFixupRange(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st, uint32_t upTo, uint32_t endLo, uint32_t endHi, bool last)
 {
-    launchDependent(ctx, true, fixupKernel, (wl->nChunks + FIX_TPB - 1) / FIX_TPB, FIX_TPB, st, wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead,
-                    wl->chunkTail, wl->chunkTailJob, wl->nChunks, wl->outGlobal, wl->outLocal, ctx->partJobs.empty() ? nullptr : wl->outTuple,
-                    ctx->err, wl->headBits, (uint32_t)(headWords(wl->nChunks) + 1), wl->searchJobs ? ~ERR_EMPTYJOB : ~0);
+    const uint32_t look = last ? wl->nChunks : upTo;
+    launchDependent(ctx, true, fixupKernel, (look + FIX_TPB - 1) / FIX_TPB, FIX_TPB, st, wl->info, wl->nJobs, wl->totalJobBlocks, wl->chunkHead,
+                    wl->chunkTail, wl->chunkTailJob, look, wl->outGlobal, wl->outLocal, ctx->partJobs.empty() ? nullptr : wl->outTuple,
+                    ctx->err, wl->headBits, (uint32_t)(headWords(wl->nChunks) + 1), wl->searchJobs ? ~ERR_EMPTYJOB : ~0, endLo, endHi, last ? 1 : 0);
 }
+
+static void launchFixup(gat_ctx *ctx, gat_worklist *wl, cudaStream_t st) { launchFixupRange(ctx, wl, st, wl->nChunks, 0u, 0xffffffffu, true); }
 
 extern "C" int gat_worklist_run(gat_ctx *ctx, gat_worklist *wl)
 {
@@ -685,14 +692,14 @@ static int rejectWorklist(int err)
 // instantiation, which looks the job of a block up in the CSR.  gat_worklist_create sees them on the host; for a
 // one-shot list jobPrepKernel reports them (ERR_EMPTYJOB: the ordinary kernel leaves at once), and the list, still on
 // the device, is scored again here with the SEARCH instantiation: no copy back, no host filter, no buffers.
-extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local)
+// scores of jobs [firstJob, nJobs) (the delta-coded calls copy the jobs of a slice back while later slices arrive)
+static int fetchResults(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local, uint64_t firstJob)
 {
-    if (!ctx || !wl) return fail(GAT_EINVAL, "gat_worklist_results: NULL argument");
-    CU(cudaSetDevice(ctx->device));
     for (int pass = 0; pass < 2; pass++) {
-        if (wl->nJobs) {
-            if (global) CU(cudaMemcpyAsync(global, wl->outGlobal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-            if (local) CU(cudaMemcpyAsync(local, wl->outLocal, wl->nJobs * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        if (wl->nJobs > firstJob) {
+            const uint64_t n = wl->nJobs - firstJob;
+            if (global) CU(cudaMemcpyAsync(global + firstJob, wl->outGlobal + firstJob, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            if (local) CU(cudaMemcpyAsync(local + firstJob, wl->outLocal + firstJob, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         }
         const std::vector<uint32_t> &parts = ctx->partJobs;          // a request covers one scoring call
         if (!parts.empty()) {
@@ -707,6 +714,7 @@ extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *glo
         if (err & ~ERR_EMPTYJOB) { ctx->partJobs.clear(); return rejectWorklist(err); }
         if (err & ERR_EMPTYJOB) {           // first sight of an empty job in this list: once more, looking jobs up
             wl->searchJobs = true;
+            firstJob = 0;
             rc = gat_worklist_run(ctx, wl);
             if (rc != GAT_OK) { ctx->partJobs.clear(); return rc; }
             continue;
@@ -719,6 +727,13 @@ extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *glo
         if ((uint64_t)ctx->partOut[k].c == 0x8080808080808080ull)
             return fail(GAT_EINVAL, "gat_request_tuples: job %u owns fewer than GAT_TUPLE_MIN_BLOCKS job-blocks", parts[k]);
     return finishStats(ctx);
+}
+
+extern "C" int gat_worklist_results(gat_ctx *ctx, gat_worklist *wl, int64_t *global, int64_t *local)
+{
+    if (!ctx || !wl) return fail(GAT_EINVAL, "gat_worklist_results: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    return fetchResults(ctx, wl, global, local, 0);
 }
 
 extern "C" int gat_score(gat_ctx *ctx, const gat_job *jobs, uint64_t nJobs, uint64_t totalJobBlocks,
@@ -797,6 +812,8 @@ static int scoreDeltaCoded(gat_ctx *ctx, const char *who, const gat_cjob *jobs, 
         if (packed) expandBlocksKernel<true><<<groups, CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, dBase, wl->blocks, firstGroup, ctx->err);
         else expandBlocksKernel<false><<<groups, CX_TPB, 0, st>>>(dBlocks, nBlocks, dAbs, nAbs, dAnch, dBase, wl->blocks, firstGroup, ctx->err);
     };
+    uint64_t doneJobs = 0;              // jobs whose scores are already on their way back (sliced lists)
+    bool fixedUp = false;
     const bool prof = ctx->profiling;
     ctx->stats.chunks = wl->nChunks;
     ctx->stats.long_streamed = wl->streamLong ? 1u : 0u;
@@ -807,6 +824,8 @@ static int scoreDeltaCoded(gat_ctx *ctx, const char *who, const gat_cjob *jobs, 
     if (slices > 1 && !ctx->copyStream) {
         CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
         for (auto &e : ctx->sliceEv) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&ctx->backStream, cudaStreamNonBlocking));
+        for (auto &e : ctx->fixEv) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     cudaStream_t cp = slices > 1 ? ctx->copyStream : st;
     if (prof) cudaEventRecord(ctx->ev[4], st);
@@ -838,6 +857,14 @@ static int scoreDeltaCoded(gat_ctx *ctx, const char *who, const gat_cjob *jobs, 
             if (rc != GAT_OK) return rc;
             const uint64_t groupsPerSlice = (nGroups + slices - 1) / slices;
             uint32_t sliceLaunches = 0;
+            // The fix-up runs per slice and finishes the jobs that end in it, so their scores go back over PCIe (the other
+            // direction, a stream of its own) while later slices still arrive -- when the caller's arrays are pinned: a copy
+            // into pageable memory would hold this thread up instead.
+            cudaPointerAttributes pa;
+            const bool early = global && local && cudaPointerGetAttributes(&pa, global) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                               cudaPointerGetAttributes(&pa, local) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+            uint32_t fixedChunks = 0;
             for (uint64_t s = 0; s < slices; s++) {
                 const uint64_t g0 = s * groupsPerSlice, g1 = std::min<uint64_t>(nGroups, g0 + groupsPerSlice);
                 if (g0 >= g1) break;
@@ -849,16 +876,38 @@ static int scoreDeltaCoded(gat_ctx *ctx, const char *who, const gat_cjob *jobs, 
                 const uint32_t c0 = (uint32_t)(r0 / CHUNK), c1 = (uint32_t)((r1 + CHUNK - 1) / CHUNK);       // GAT_CGROUP is a multiple of CHUNK
                 launchScoring(ctx, P, c0, c1 - c0, wl->plain, wl->streamLong, wl->searchJobs, false, st);      // (behind expandBlocksKernel: no early start)
                 sliceLaunches += 2;
+                const bool lastSlice = g1 == nGroups;
+                launchFixupRange(ctx, wl, st, c1, fixedChunks, lastSlice ? 0xffffffffu : c1, lastSlice);
+                fixedChunks = c1;
+                sliceLaunches += 1;
+                if (early && !lastSlice && !wl->searchJobs) {
+                    // jobs [doneJobs, upTo) end in chunks below c1, i.e. own no record at or behind record c1 * CHUNK
+                    const uint64_t limit = (uint64_t)c1 * CHUNK;
+                    uint64_t lo = doneJobs, hi = nJobs;         // first job j with end(j) > limit; end(j) = blockPtr[j + 1] (or nBlocks)
+                    while (lo < hi) {
+                        const uint64_t mid = (lo + hi) / 2, end = mid + 1 < nJobs ? jobs[mid + 1].blockPtr : nBlocks;
+                        if (end <= limit) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo > doneJobs) {
+                        CU(cudaEventRecord(ctx->fixEv[s], st));
+                        CU(cudaStreamWaitEvent(ctx->backStream, ctx->fixEv[s], 0));
+                        CU(cudaMemcpyAsync(global + doneJobs, wl->outGlobal + doneJobs, (lo - doneJobs) * sizeof(long long), cudaMemcpyDeviceToHost, ctx->backStream));
+                        CU(cudaMemcpyAsync(local + doneJobs, wl->outLocal + doneJobs, (lo - doneJobs) * sizeof(long long), cudaMemcpyDeviceToHost, ctx->backStream));
+                        doneJobs = lo;
+                    }
+                }
             }
-            ctx->stats.kernel_launches = sliceLaunches - 2;
+            ctx->stats.kernel_launches = sliceLaunches - 3;
+            fixedUp = true;
         }
-        launchFixup(ctx, wl, st);
+        if (!fixedUp) launchFixup(ctx, wl, st);
         if (prof) CU(cudaEventRecord(ctx->ev[3], st));
-        ctx->stats.kernel_launches += 5;        // expandJobs, expandBlocks, jobPrep, scoreChunks, fixup (+ 2 per further slice)
+        ctx->stats.kernel_launches += 5;        // expandJobs, expandBlocks, jobPrep, scoreTiles, fixup (+ 3 per further slice)
     }
     CU(cudaGetLastError());
     if (prof) cudaEventRecord(ctx->ev[5], st);
-    rc = gat_worklist_results(ctx, wl, global, local);
+    if (doneJobs) CU(cudaStreamSynchronize(ctx->backStream));      // (before anything else may write the caller's arrays)
+    rc = fetchResults(ctx, wl, global, local, doneJobs);
     if (rc == GAT_OK && prof && wl->nChunks) {
         float total = 0;
         cudaEventElapsedTime(&total, ctx->ev[4], ctx->ev[0]);

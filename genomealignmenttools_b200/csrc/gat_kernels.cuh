@@ -512,6 +512,7 @@ __device__ __noinline__ void warpJobReduceWide(const ScoreParams &P, const int (
 
 // ------------------------------------------------------------------ cross-chunk fix-up
 // A job that starts in chunk c and ends in chunk c' > c:  tail(c) + head(c+1) + ... + head(c').
+// (nChunks = chunks this launch looks at: all of them, or those of the slices that have been scored so far.)
 // One thread per chunk.  Most open tails end within a few chunks: the thread folds those itself.  A job
 // that runs over many chunks is folded by the whole CTA, one contiguous slice of heads per thread.
 constexpr int FIX_TPB = 256;
@@ -547,7 +548,7 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
             const Tup *__restrict__ chunkHead, const Tup *__restrict__ chunkTail,
             const int *__restrict__ chunkTailJob, uint32_t nChunks,
             long long *__restrict__ outGlobal, long long *__restrict__ outLocal, Tup *__restrict__ outTuple, const int *__restrict__ err,
-            uint32_t *__restrict__ headBits, uint32_t headBitsWords, int fatal)
+            uint32_t *__restrict__ headBits, uint32_t headBitsWords, int fatal, uint32_t endLo, uint32_t endHi, int clearBits)
 {
     __shared__ uint32_t sLongC[FIX_TPB], sLongN[FIX_TPB];
     __shared__ int sLongJ[FIX_TPB];
@@ -559,7 +560,7 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
     dependentsMayLaunch();
     // the job-start bitmap goes back to all-zero for the next pass (jobPrepKernel sets bits with atomicOr; the words
     // behind the last chunk hold the closing bit, the slack and the mode word)
-    if (c < nChunks) {
+    if (clearBits && c < nChunks) {
         uint4 *w = reinterpret_cast<uint4 *>(headBits + (size_t)c * (CHUNK / 32));
         w[0] = make_uint4(0u, 0u, 0u, 0u); w[1] = make_uint4(0u, 0u, 0u, 0u);
         if (c + 1 == nChunks)
@@ -572,7 +573,13 @@ fixupKernel(const JobInfo *__restrict__ info, unsigned long long nJobs, unsigned
     uint32_t count = 0;                                 // heads to fold: chunks c+1 .. c+count
     if (c < nChunks) {
         j = chunkTailJob[c];
-        if (j >= 0) count = (uint32_t)((info[j + 1].blockPtr - 1) / CHUNK) - c;
+        if (j >= 0) {
+            const uint32_t endChunk = (uint32_t)((info[j + 1].blockPtr - 1) / CHUNK);
+            count = endChunk - c;
+            // a work-list that arrives in slices is fixed up slice by slice: this launch finishes the jobs that end in chunks
+            // [endLo, endHi) and leaves the others to the launch that covers their last chunk
+            if (endChunk < endLo || endChunk >= endHi) j = -1;
+        }
     }
     if (j >= 0) {
         if (count <= FIX_SERIAL) {

@@ -521,6 +521,17 @@ def test_packed_worklist_scores_like_plain(n_blocks, kw):
         g, l = sc.score(w.jobs, w.total, blocks)
         pg, pl = sc.score_packed(cj, pb, ab, an, base)
         assert np.array_equal(g, pg) and np.array_equal(l, pl)
+        if n_blocks > 100000:   # pinned result arrays: the scores of a slice's jobs come back while later slices arrive
+            from genomealignmenttools_b200.engine import PinnedArray
+            from genomealignmenttools_b200.records import pack_compact, split_long_blocks
+            hg, hl = PinnedArray(len(cj), np.int64), PinnedArray(len(cj), np.int64)
+            hg.array[:] = -7; hl.array[:] = -7
+            sc.score_packed(cj, pb, ab, an, base, hg.array, hl.array)
+            assert np.array_equal(g, hg.array) and np.array_equal(l, hl.array)
+            hg.array[:] = -7; hl.array[:] = -7
+            sc.score_compact(*pack_compact(*split_long_blocks(w.jobs, w.total, blocks, 4096)), hg.array, hl.array)
+            assert np.array_equal(g, hg.array) and np.array_equal(l, hl.array)
+            hg.free(); hl.free()
         if len(ab) > 1:         # a table that is too short is rejected, and the context survives
             with pytest.raises(GatError):
                 sc.score_packed(cj, pb, ab[:-1], an, base)
