@@ -119,10 +119,15 @@ def h2d_ceiling(torch, device, barrier, nbytes=256 << 20, reps=5):
 def source_hash():
     """Hash of the kernel sources: a DRAM-traffic figure measured under ncu (profiles/traffic.json, written by
     tools/measure_traffic.sh) is only quoted for the code it was measured on."""
-    import hashlib
+    import hashlib, re
     h = hashlib.sha256()
     for f in ("gat_tiles.cuh", "gat_kernels.cuh", "gat_capi.cu"):
-        h.update(open(os.path.join(ROOT, "genomealignmenttools_b200", "csrc", f), "rb").read())
+        text = open(os.path.join(ROOT, "genomealignmenttools_b200", "csrc", f), "r", errors="replace").read()
+        # the code, not its commentary: // comments, /* */ comments and blank lines do not count (no string literal of these
+        # files holds "//" or "/*")
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        lines = [re.sub(r"//.*$", "", ln).rstrip() for ln in text.splitlines()]
+        h.update("\n".join(ln for ln in lines if ln.strip()).encode())
     return h.hexdigest()[:16]
 
 

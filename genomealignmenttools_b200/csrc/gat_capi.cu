@@ -1,5 +1,5 @@
 // gat_capi.cu -- the C ABI of include/gat.h on top of the kernels in gat_kernels.cuh.
-// No CPU scoring path exists in this library: every score comes out of scoreChunksKernel.
+// No CPU scoring path exists in this library: every score comes out of scoreTilesKernel (gat_tiles.cuh).
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>

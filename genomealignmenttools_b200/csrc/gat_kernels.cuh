@@ -429,7 +429,7 @@ template <typename T> __device__ __forceinline__ long long finalLocal(const TupT
 }
 __device__ __forceinline__ long long finalLocal(const Tup &t) { return max64(0, max64(max64(t.c, t.d), max64(t.e, t.f))); }
 
-// Phase 3 of scoreChunksKernel for one warp (see there), in 32- or 64-bit tuples.  Lane l holds job-blocks
+// Phase 3 of scoreTilesKernel for one warp (see gat_tiles.cuh), in 32- or 64-bit tuples.  Lane l holds job-blocks
 // 4l..4l+3 of the warp: scores a[], gap costs g[] (the gap BEFORE the block), flags fl4 (one byte each).
 template <typename T, bool SEARCH>
 __device__ __forceinline__ void warpJobReduce(const ScoreParams &P, const int (&a)[BPT], const int (&g)[BPT], uint32_t fl4,

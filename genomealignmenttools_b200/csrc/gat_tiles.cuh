@@ -1,6 +1,6 @@
-// gat_tiles.cuh -- second-generation scoring kernel (sm_100a): scoreTilesKernel.
+// gat_tiles.cuh -- the scoring kernel (sm_100a): scoreTilesKernel.
 //
-// Same job as scoreChunksKernel in gat_kernels.cuh -- kent chainCalcScore / chainScoreBlock
+// Same job as round 1's scoreChunksKernel (gone) -- kent chainCalcScore / chainScoreBlock
 // (kent/src/lib/chainConnect.c:14-40), gapCalcCost (kent/src/lib/gapCalc.c:298-331), hillerlab
 // chainCalcScoreLocal (src/scoreChain/scoreChain.c:176-198) and the clip of chainFastSubsetOnT
 // (kent/src/lib/chain.c:510-522) -- and the same decomposition (a warp owns a tile of 128 job-blocks,
@@ -16,7 +16,8 @@
 //  * PLAIN work-lists (whole chains, no clip) read a 16-byte job descriptor and skip the clip arithmetic;
 //  * every list slot is stored pre-biased (word index minus its position in the list), so an item is
 //    `slot + i`: no per-item subtraction, no second shared-memory look-up;
-//  * the item-head bitmap is written while the list is built (one shared atomic per listed block);
+//  * the slots that start inside a round of the item list come from one warp-wide OR (REDUX) of "my slot starts at
+//    position p": no item-head bitmap in shared memory, no atomics;
 //  * one dense gap table (small gaps included) and an N summary stored as overlapping word pairs: one
 //    load and a funnel shift per test, no branches in front of the loads;
 //  * all loads of a sub-tile (genome windows, N summary, gap cost) are issued before any is consumed;
