@@ -407,10 +407,11 @@ scoreTilesKernel(const __grid_constant__ ScoreParams P)
 
     // ---- phase 1: the tile's job-blocks, 32 at a time, lane = block.  Each sub-tile is handled in two halves: front()
     // reads the records, validates them and issues every global load the sub-tile needs (first window of both genomes,
-    // N summaries, gap cost); back() builds the item list and only then consumes the loads.  The halves of neighbouring
-    // sub-tiles are interleaved (front 0, front 1, back 0, front 2, back 1, ...), so two sub-tiles' loads are in flight per
-    // warp and the shuffle chain of the list prefix runs under the memory latency.  The four sub-tiles are unrolled (every
-    // shared-memory offset an immediate) unless the instantiation streams long blocks (see streamLongBlocks).
+    // N summaries, gap cost); back() builds the item list and only then consumes the loads, so the shuffle chain of the
+    // list prefix runs under the memory latency.  Sub-tiles go one after the other (front s, back s; the next sub-tile's job
+    // descriptor is fetched a sub-tile ahead): keeping two sub-tiles' loads in flight needs 80 registers and was slower
+    // (profiles/README.md).  The four sub-tiles are unrolled (every shared-memory offset an immediate) unless the
+    // instantiation streams long blocks (see streamLongBlocks).
     uint32_t seen = 0;                  // 1: some block of mine may contain N, 2: some block of mine is big (see back())
     int nSlots = 0;                     // blocks of this tile with more than 32 bases: they get a slot in the item list
     uint32_t itemBase = 0;              // items of the list so far
